@@ -1,0 +1,143 @@
+/* include/hsflow.h -- C ABI of libhsflow.so, the B200-native Horn-Schunck engine.
+ *
+ * This is the drop-in boundary for the hot path of miczi/OpticalFlowHS.  The reference has
+ * no FFI of its own: its boundary is the C++ class HSOpticalFlowOpenCL (HSOpticalFlowOpenCL.hpp:26-264)
+ * sitting on the OpenCL C API.  include/HSOpticalFlowOpenCL.hpp re-declares that class for the
+ * unchanged main.cpp and implements it on the entry points below; every entry point cites the
+ * reference code it replaces (paths relative to /root/reference/OpticalFlowHS/).
+ *
+ * Conventions: plain C types only; every function returns 0 (HSFLOW_OK) or a negative
+ * HSFLOW_E* code, with a thread-local message in hsflow_last_error().  There is NO CPU
+ * fallback: without a CUDA device hsflow_create() fails with HSFLOW_ENODEV.
+ * All work of one handle is ordered on that handle's CUDA stream; calls taking host
+ * pointers marked "sync" return when the data is usable, everything else is asynchronous
+ * until hsflow_sync().
+ */
+#ifndef HSFLOW_H_
+#define HSFLOW_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
+#endif
+
+typedef struct hsflow hsflow_t;
+
+enum {
+    HSFLOW_OK = 0,
+    HSFLOW_EINVAL = -1,  /* bad argument / call order */
+    HSFLOW_ENODEV = -2,  /* no usable CUDA device (sm_100) */
+    HSFLOW_ECUDA = -3,   /* CUDA runtime / driver error, see hsflow_last_error() */
+    HSFLOW_ENOMEM = -4
+};
+
+/* neighbourhood of the smoothness average (BASELINE.json north_star: "4- or 8-neighbour") */
+enum {
+    HSFLOW_STENCIL_CL8 = 0, /* Kernels.cl:55-63  1/6 edge + 1/12 diagonal, rho = alpha^2        */
+    HSFLOW_STENCIL_CV4 = 1  /* cvCalcOpticalFlowHS: 1/4 edge, rho = 1/lambda     */
+};
+
+/* arithmetic contract of the iteration kernels */
+enum {
+    HSFLOW_MATH_FAST = 0,  /* normalised coefficients + FMA; |du|,|dv| <= 1e-3 px vs the oracle   */
+    HSFLOW_MATH_EXACT = 1  /* operand-for-operand Kernels.cl:55-63,84-86 without contraction and
+                              with IEEE division: bit-identical to the host oracle.  T = 1 only.  */
+};
+
+/* which derivative estimator feeds the iteration */
+enum {
+    HSFLOW_DERIV_CL = 0,   /* ComputeDerivativesKernel, Kernels.cl:13-39 (2x2x2 cube)            */
+    HSFLOW_DERIV_CV = 1    /* OpenCV 2.1: 3x3 box blur of both frames, Sobel/8 on frame 1,
+                              It = frame2 - frame1 (OpticalFlowOpenCV.cpp:27-29)  */
+};
+
+enum { HSFLOW_PHASE_LOAD = 0, HSFLOW_PHASE_DERIV = 1, HSFLOW_PHASE_ITER = 2, HSFLOW_PHASE_READ = 3 };
+
+/* ---- library ---------------------------------------------------------------------- */
+const char* hsflow_last_error(void);
+int hsflow_version(void);
+int hsflow_device_count(void);
+
+/* ---- lifecycle: replaces setupCL() (cpp:67-319) and cleanup() (cpp:849-892) ---------- */
+int hsflow_create(int device, hsflow_t** out);
+int hsflow_destroy(hsflow_t* h);
+/* Run on a caller-owned CUDA stream (a cudaStream_t passed as void*); NULL restores the own stream. */
+int hsflow_set_stream(hsflow_t* h, void* cuda_stream);
+
+/* ---- parameters: replaces the ctor arguments alp/it/gs (hpp:130-161) and kernel arg 7
+ *      (cpp:617-621).  temporal_block = Jacobi iterations fused per launch (0 = auto). ---- */
+int hsflow_set_params(hsflow_t* h, float alpha, int iterations, int stencil, int update_v, int temporal_block);
+int hsflow_set_lambda(hsflow_t* h, float lambda);         /* rho = 1/lambda (cv.cpp:29)          */
+int hsflow_set_math(hsflow_t* h, int math_mode);          /* HSFLOW_MATH_*                      */
+int hsflow_set_deriv(hsflow_t* h, int deriv_mode);        /* HSFLOW_DERIV_*                     */
+int hsflow_set_tuning(hsflow_t* h, int chunk_rows, int warps_per_cta, int sub_batch); /* 0 = auto */
+int hsflow_set_warm_start(hsflow_t* h, int keep_uv);      /* use_previous (cv.h:481-483)        */
+/* 0 = auto; 1 = single-sweep kernel only (one launch per iteration); 2 = streaming kernel even for T = 1 */
+int hsflow_set_kernel(hsflow_t* h, int which);
+
+/* ---- geometry: W x H frames, `pairs` independent frame pairs per handle ------------------ */
+int hsflow_configure(hsflow_t* h, int width, int height, int pairs);
+/* Row-strip of a taller frame: the handle's H rows are [own rows + ghost rows]; edges that are
+ * not true image edges (is_top/is_bottom = 0) are fed by the caller's halo exchange, see
+ * hsflow_iterate().  Default after configure: both are true edges. */
+int hsflow_set_strip(hsflow_t* h, int is_top_edge, int is_bottom_edge);
+
+/* ---- ingest: replaces readInputImage/readInputFrame (cpp:6-64), cvCvtColor (cpp:727-728) and the
+ *      clEnqueueWriteBuffer of both frames (cpp:339-357).  Host pointers; pitch in bytes. ------- */
+int hsflow_set_frames_gray8(hsflow_t* h, int pair, const uint8_t* f1, const uint8_t* f2, size_t pitch);
+int hsflow_set_frames_bgr8(hsflow_t* h, int pair, const uint8_t* f1, const uint8_t* f2, size_t pitch);
+int hsflow_set_frames_f32(hsflow_t* h, int pair, const float* f1, const float* f2, size_t pitch);
+/* Same with device pointers (frames already in HBM). */
+int hsflow_set_frames_gray8_dev(hsflow_t* h, int pair, const uint8_t* d_f1, const uint8_t* d_f2, size_t pitch);
+/* Device-side synthetic frames for benches and large-frame tests (bit-identical to
+ * oracle hso_synth_pair): rows [row0, row0+H) of a W x full_height frame, seed0 + pair. */
+int hsflow_synth_frames(hsflow_t* h, int full_height, int row0, uint32_t seed0);
+/* One-call form used by the class: configure(w,h,1) + set_frames(0). */
+int hsflow_load_pair_gray8(hsflow_t* h, const uint8_t* f1, const uint8_t* f2, int w, int hgt, size_t pitch);
+int hsflow_load_pair_bgr8(hsflow_t* h, const uint8_t* f1, const uint8_t* f2, int w, int hgt, size_t pitch);
+int hsflow_load_pair_f32(hsflow_t* h, const float* f1, const float* f2, int w, int hgt, size_t pitch);
+
+/* ---- compute ---------------------------------------------------------------------------
+ * hsflow_compute = the timed region of run() (cpp:748-751): runDerivatives() once, then
+ * runCLKernels() x iterations, for every pair of the handle, without the per-iteration PCIe
+ * round trip.  It is hsflow_prepare() followed by hsflow_iterate(iterations). */
+int hsflow_compute(hsflow_t* h);
+int hsflow_prepare(hsflow_t* h);            /* runDerivatives (cpp:321-474): coefficients; u = v = 0 */
+int hsflow_iterate(hsflow_t* h, int n);     /* n x runCLKernels (cpp:476-679)                         */
+/* Strip mode: after the caller refreshed the ghost rows of the current u/v planes. */
+int hsflow_halo_refreshed(hsflow_t* h);
+int hsflow_sync(hsflow_t* h);
+
+/* ---- results: replaces clEnqueueReadBuffer of u,v (cpp:655-675) / Ex,Ey,Et (cpp:437-468) - */
+int hsflow_read_uv(hsflow_t* h, int pair, float* u, float* v, size_t pitch);              /* sync */
+int hsflow_read_derivatives(hsflow_t* h, int pair, float* Ex, float* Ey, float* Et, size_t pitch); /* sync */
+int hsflow_write_uv(hsflow_t* h, int pair, const float* u, const float* v, size_t pitch); /* warm start */
+/* Current device planes: element pitch of a row and of a pair (floats). */
+int hsflow_get_device_uv(hsflow_t* h, float** d_u, float** d_v, size_t* row_pitch, size_t* pair_pitch);
+int hsflow_get_device_frames(hsflow_t* h, uint8_t** d_f1, uint8_t** d_f2, size_t* row_pitch, size_t* pair_pitch);
+/* Drawing predicate of cpp:762-765 on the device: mask[(i/step)*ceil(W/step) + j/step]. */
+int hsflow_dot_mask(hsflow_t* h, int pair, int step, float threshold, uint8_t* mask, int* count); /* sync */
+
+/* ---- pipelined host-to-host batch: H2D, compute and D2H of consecutive pairs overlap --------
+ * frames: n_pairs x 2 gray8 images (f1 then f2, densely packed W*H each) in host memory;
+ * u_out/v_out: n_pairs x W*H floats.  Pinned host memory gives full PCIe rate. */
+int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out);
+
+/* ---- instrumentation ------------------------------------------------------------------ */
+float hsflow_last_ms(hsflow_t* h, int phase);         /* CUDA-event time of the last call's phase  */
+long long hsflow_kernel_launches(hsflow_t* h);        /* kernels launched by this handle so far    */
+int hsflow_effective_temporal_block(hsflow_t* h);
+void* hsflow_alloc_pinned(size_t bytes);              /* cudaMallocHost / cudaFreeHost helpers     */
+void hsflow_free_pinned(void* p);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSFLOW_H_ */

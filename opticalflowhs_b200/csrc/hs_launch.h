@@ -1,0 +1,76 @@
+// hs_launch.h -- argument blocks and host-side launchers shared by the kernels and the C ABI.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hs {
+
+struct DerivArgs {
+    const uint8_t* f1;          // frame planes [pair][row][bytes]
+    const uint8_t* f2;
+    long long f_row_pitch;      // bytes
+    long long f_pair_pitch;     // bytes
+    float* c0;                  // Ex|a, Ey|b, Et|c planes [pair][row][col]
+    float* c1;
+    float* c2;
+    long long c_row_pitch;      // elements
+    long long c_pair_pitch;     // elements
+    int W, H;
+    int normalise;              // 1: write a,b,c = (Ex,Ey,Et)/sqrt(rho+Ex^2+Ey^2); 0: raw derivatives
+    float rho;                  // alpha^2 (Kernels.cl:85) or 1/lambda
+};
+
+struct Jacobi1Args {
+    const float* u_in;
+    const float* v_in;
+    float* u_out;
+    float* v_out;
+    const float* c0;
+    const float* c1;
+    const float* c2;
+    long long row_pitch;        // elements, common to all planes
+    long long in_pair_pitch, out_pair_pitch, c_pair_pitch;
+    int W, H;                   // H = rows of the buffer (replicate beyond both ends)
+    int out_lo, out_hi;         // rows to produce
+    int chunk_rows;
+    float rho;                  // EXACT only
+};
+
+struct StreamArgs {
+    float* u_out;
+    float* v_out;
+    long long row_pitch;        // elements
+    long long out_pair_pitch;
+    int W, H;
+    int out_lo, out_hi;
+    int chunk_rows;
+    int nsx, ncy;
+    int z_in0, z_c0;            // first pair index inside the u/v source map and the coefficient maps
+    long long total_units;
+};
+
+struct StreamGeom {             // filled by stream_geometry()
+    int halo, valid_w, smem_per_warp, max_T;
+};
+
+cudaError_t launch_deriv(const DerivArgs& A, int fmt, int pairs, cudaStream_t s);
+cudaError_t launch_box3(const uint8_t* src, uint8_t* dst, int W, int H, long long rp, long long pp, int pairs, cudaStream_t s);
+cudaError_t launch_deriv_cv(const DerivArgs& A, int pairs, cudaStream_t s);
+cudaError_t launch_jacobi1(const Jacobi1Args& A, bool exact, int stencil, bool update_v, int pairs, cudaStream_t s);
+cudaError_t launch_synth(uint8_t* f1, uint8_t* f2, int W, int rows, int full_h, int row0, long long rp, long long pp,
+                         uint32_t seed0, int pairs, cudaStream_t s);
+cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long long pitch, int step, float thr,
+                            uint8_t* mask, int* count, cudaStream_t s);
+
+// temporally blocked streaming kernel (hs_stream.cu)
+constexpr int kMaxT = 8;
+constexpr int kStreamRowsPerBox = 2;   // TMA box = 128 columns x 2 rows
+StreamGeom stream_geometry(int T);
+cudaError_t stream_prepare(int device);     // opt in to large dynamic shared memory for every instantiation
+// maps: u source, v source, coefficient planes a,b,c.  warps_per_cta in 1..8.
+cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tm_u, const CUtensorMap& tm_v,
+                                 const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_c,
+                                 StreamArgs A, int pairs, int warps_per_cta, cudaStream_t s);
+
+}  // namespace hs

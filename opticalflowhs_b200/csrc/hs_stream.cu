@@ -1,0 +1,337 @@
+// hs_stream.cu -- temporally blocked Horn-Schunck iteration for sm_100a (B200).
+//
+// Replaces T consecutive runCLKernels() calls (HSOpticalFlowOpenCL.cpp:476-679: H2D u,v ->
+// u_v_avgKernel -> u_v_updateKernel -> D2H u,v; Kernels.cl:43-90) by ONE launch that reads
+// u, v and the three coefficient planes once and writes u, v once.
+//
+// Design (B200-first, HBM-bound fp32 stencil -- no tensor cores on purpose):
+//  * work unit = one WARP x (128-column strip, row chunk, frame pair).  Warps are autonomous:
+//    own shared-memory rings, own mbarriers, no __syncthreads anywhere.
+//  * TMA (cp.async.bulk.tensor.3d, one elected lane) stages 128 x RG row boxes of u, v
+//    (source planes) and a, b, c (normalised coefficients) into per-warp rings; out-of-image
+//    columns are zero-filled by the TMA unit and then re-clamped in registers (Neumann border,
+//    Tex2D Kernels.cl:2-9), so the kernel has no bounds checks on loads.
+//  * the warp streams DOWN the rows.  Each lane owns 4 adjacent columns.  Time step s+1 of row
+//    r-1 is produced as soon as time step s of row r exists, so T time steps are in flight as a
+//    register pipeline: per stage and field only two partial sums per pixel are kept
+//    (p = G(r-1) + 2h(r), g = G(r); see hs_common.cuh), 16 registers per stage.
+//  * left/right neighbours come from warp shuffles (one __shfl_up + one __shfl_down per field
+//    and stage-row); the strip carries a halo of HL >= T columns on each side that absorbs the
+//    shrinking valid region, the chunk carries T warm-up rows above and below.
+//  * results leave through coalesced 16-byte stores of the strip's valid columns.
+// Per pixel-iteration: 14 FP32 instructions, 1 shuffle, 12 B of shared-memory reads; HBM
+// traffic 28 B / T per pixel-iteration (+ halo overhead).  tests/stream_model.py is the numpy
+// model of exactly this bookkeeping.
+#include <type_traits>
+
+#include "hs_common.cuh"
+#include "hs_launch.h"
+
+namespace hs {
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 22)) __trap();   // a lost TMA transaction must fail loudly, never hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// ---- geometry ------------------------------------------------------------------------------------
+template <int T, int RG, int NGC, int NGUV> struct StreamCfg {
+    static constexpr int HL = (T + 3) / 4 * 4;              // column halo per side, multiple of 4
+    static constexpr int VALIDW = kStripW - 2 * HL;         // columns a strip produces
+    static constexpr int NRC = NGC * RG;                    // coefficient ring rows
+    static constexpr int NRUV = NGUV * RG;                  // u/v ring rows
+    static constexpr int ROWB = kStripW * 4;                // bytes per ring row
+    static constexpr int SMEM_WARP = (3 * NRC + 2 * NRUV) * ROWB + 128;   // + mbarriers
+    static_assert(NGC * RG > T + RG, "coefficient ring too short for the stage lag");
+    static_assert(NGC + NGUV <= 16, "barrier block is 128 bytes");
+};
+template <int T> struct DefaultCfg {
+    static constexpr int RG = kStreamRowsPerBox;
+    static constexpr int NGC = (T + RG - 1) / RG + 2;
+    static constexpr int NGUV = 3;
+    using type = StreamCfg<T, RG, NGC, NGUV>;
+};
+
+// ---- the kernel -----------------------------------------------------------------------------------
+template <int T, int ST>
+__global__ void __launch_bounds__(256)
+k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
+                const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const __grid_constant__ CUtensorMap tm_c, const StreamArgs A) {
+    using C = typename DefaultCfg<T>::type;
+    constexpr int RG = DefaultCfg<T>::RG, NGC = DefaultCfg<T>::NGC, NGUV = DefaultCfg<T>::NGUV;
+    constexpr int NRC = C::NRC, NRUV = C::NRUV;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long unit = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (unit >= A.total_units) return;
+    const int sx = (int)(unit % A.nsx);
+    const long long tt = unit / A.nsx;
+    const int cy = (int)(tt % A.ncy);
+    const int z = (int)(tt / A.ncy);
+    const int W = A.W, H = A.H;
+    const int R0 = A.out_lo + cy * A.chunk_rows;
+    const int R1 = min(R0 + A.chunk_rows, A.out_hi);
+    const int x0 = sx * C::VALIDW - C::HL;
+    const int col0 = x0 + lane * 4;
+    const int rs = max(R0 - T, 0);                 // first input row streamed
+    const int last_tick = R1 - 1 + T;              // tick at which row R1-1 of time T is produced
+    const int last_in = min(last_tick, H - 1);     // last real input row
+    const int g0 = rs / RG, glast = last_in / RG;  // TMA row groups (absolute, RG-aligned)
+    const int base = g0 * RG;
+    const bool edge = (sx == 0) || (x0 + kStripW - 1 >= W - 1);
+    const bool wmis = (W & 3) != 0;
+
+    float* sa = reinterpret_cast<float*>(smem_raw + (size_t)warp * C::SMEM_WARP);
+    float* sb = sa + NRC * kStripW;
+    float* sc = sb + NRC * kStripW;
+    float* su = sc + NRC * kStripW;
+    float* sv = su + NRUV * kStripW;
+    const uint32_t bar0 = smem_u32(sv + NRUV * kStripW);   // cbar[NGC] then uvbar[NGUV]
+    const uint32_t sa32 = smem_u32(sa), sb32 = smem_u32(sb), sc32 = smem_u32(sc), su32 = smem_u32(su), sv32 = smem_u32(sv);
+
+    auto issue_coef = [&](int g) {                 // lane 0 only
+        const int slot = (g - g0) % NGC;
+        const uint32_t bar = bar0 + 8u * slot;
+        mbar_expect_tx(bar, 3u * RG * C::ROWB);
+        const uint32_t off = (uint32_t)slot * RG * C::ROWB;
+        tma_load_3d(sa32 + off, &tm_a, x0, g * RG, A.z_c0 + z, bar);
+        tma_load_3d(sb32 + off, &tm_b, x0, g * RG, A.z_c0 + z, bar);
+        tma_load_3d(sc32 + off, &tm_c, x0, g * RG, A.z_c0 + z, bar);
+    };
+    auto issue_uv = [&](int g) {                   // lane 0 only
+        const int slot = (g - g0) % NGUV;
+        const uint32_t bar = bar0 + 8u * (NGC + slot);
+        mbar_expect_tx(bar, 2u * RG * C::ROWB);
+        const uint32_t off = (uint32_t)slot * RG * C::ROWB;
+        tma_load_3d(su32 + off, &tm_u, x0, g * RG, A.z_in0 + z, bar);
+        tma_load_3d(sv32 + off, &tm_v, x0, g * RG, A.z_in0 + z, bar);
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NGC + NGUV; ++i) mbar_init(bar0 + 8u * i, 1);
+        fence_mbar_init();
+#pragma unroll
+        for (int k = 0; k < NGUV; ++k)
+            if (g0 + k <= glast) issue_uv(g0 + k);
+#pragma unroll
+        for (int k = 0; k < NGC; ++k)
+            if (g0 + k <= glast) issue_coef(g0 + k);
+    }
+    __syncwarp();
+
+    // register pipeline: per stage, field (u: 0..3, v: 4..7) and pixel two partial sums
+    float p[T][8], g[T][8];
+#pragma unroll
+    for (int s = 0; s < T; ++s)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { p[s][j] = 0.f; g[s][j] = 0.f; }
+
+    const bool lane_out = (lane >= C::HL / 4) && (lane < 32 - C::HL / 4) && (col0 < W);
+    float* uo = A.u_out + (size_t)z * A.out_pair_pitch + col0;
+    float* vo = A.v_out + (size_t)z * A.out_pair_pitch + col0;
+
+    auto tick = [&](auto gen_tag, const int r) {
+        constexpr bool GEN = decltype(gen_tag)::value;
+        const int rr = r - base;                   // row relative to the first TMA group
+        float cu[4], cv[4];
+        bool have = false;
+        if (!GEN || r <= H - 1) {
+            if ((rr % RG) == 0 || r == rs) {       // first row consumed from this group
+                const int gr = rr / RG;
+                mbar_wait(bar0 + 8u * (NGC + gr % NGUV), (gr / NGUV) & 1);
+                mbar_wait(bar0 + 8u * (gr % NGC), (gr / NGC) & 1);
+            }
+            const int q = rr % NRUV;
+            const float4 tu = lds128(su + q * kStripW + lane * 4);
+            const float4 tv = lds128(sv + q * kStripW + lane * 4);
+            cu[0] = tu.x; cu[1] = tu.y; cu[2] = tu.z; cu[3] = tu.w;
+            cv[0] = tv.x; cv[1] = tv.y; cv[2] = tv.z; cv[3] = tv.w;
+            have = true;
+        }
+#pragma unroll
+        for (int S = 0; S < T; ++S) {
+            const int rho = r - S;                 // row of time step S this stage receives
+            bool virt = false;
+            if (GEN) {
+                if (rho < rs || rho > H) have = false;
+                else if (rho == H) { virt = true; have = true; }   // row H == row H-1 (clamp)
+                if (!have) continue;
+            }
+            float ub[4], vb[4];
+            if (GEN && virt) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ub[j] = combine<ST>(p[S][j], g[S][j]);
+                    vb[j] = combine<ST>(p[S][4 + j], g[S][4 + j]);
+                }
+            } else {
+                if (edge && wmis) { sanitize_right(cu, col0, W); sanitize_right(cv, col0, W); }
+                float lu = __shfl_up_sync(kFull, cu[3], 1), ru = __shfl_down_sync(kFull, cu[0], 1);
+                float lv = __shfl_up_sync(kFull, cv[3], 1), rv = __shfl_down_sync(kFull, cv[0], 1);
+                if (edge) { clamp_lr(cu, col0, W, lu, ru); clamp_lr(cv, col0, W, lv, rv); }
+                const float hu[4] = {__fadd_rn(lu, cu[1]), __fadd_rn(cu[0], cu[2]), __fadd_rn(cu[1], cu[3]), __fadd_rn(cu[2], ru)};
+                const float hv[4] = {__fadd_rn(lv, cv[1]), __fadd_rn(cv[0], cv[2]), __fadd_rn(cv[1], cv[3]), __fadd_rn(cv[2], rv)};
+                if (GEN && rho == rs) {            // first row of this stage: replicate upwards
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float Gu = rowG<ST>(cu[j], hu[j]), Gv = rowG<ST>(cv[j], hv[j]);
+                        p[S][j] = pOf<ST>(Gu, hu[j]); g[S][j] = Gu;
+                        p[S][4 + j] = pOf<ST>(Gv, hv[j]); g[S][4 + j] = Gv;
+                    }
+                    have = false;
+                    continue;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float Gu = rowG<ST>(cu[j], hu[j]), Gv = rowG<ST>(cv[j], hv[j]);
+                    ub[j] = combine<ST>(p[S][j], Gu);
+                    vb[j] = combine<ST>(p[S][4 + j], Gv);
+                    p[S][j] = pOf<ST>(g[S][j], hu[j]); g[S][j] = Gu;
+                    p[S][4 + j] = pOf<ST>(g[S][4 + j], hv[j]); g[S][4 + j] = Gv;
+                }
+            }
+            // time step S+1 of row rho-1 (coefficients of that row)
+            const int q = (rr - S - 1 + 2 * NRC) % NRC;
+            const float4 ka = lds128(sa + q * kStripW + lane * 4);
+            const float4 kb = lds128(sb + q * kStripW + lane * 4);
+            const float4 kc = lds128(sc + q * kStripW + lane * 4);
+            update_fast(ub[0], vb[0], ka.x, kb.x, kc.x, cu[0], cv[0]);
+            update_fast(ub[1], vb[1], ka.y, kb.y, kc.y, cu[1], cv[1]);
+            update_fast(ub[2], vb[2], ka.z, kb.z, kc.z, cu[2], cv[2]);
+            update_fast(ub[3], vb[3], ka.w, kb.w, kc.w, cu[3], cv[3]);
+        }
+        const int ro = r - T;
+        if (have && lane_out && ro >= R0 && ro < R1) {
+            const size_t o = (size_t)ro * A.row_pitch;
+            *reinterpret_cast<float4*>(uo + o) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+            *reinterpret_cast<float4*>(vo + o) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        }
+        // Ring refills, after every lane consumed its shared-memory reads of this tick:
+        //  * the u/v group whose last row was read by stage 0 in this tick,
+        //  * the coefficient group whose last row (r-T) was used by the last stage in this tick.
+        const int qq = rr - T;
+        const bool refill_uv = (r <= H - 1) && (rr % RG) == RG - 1;
+        const bool refill_c = qq >= 0 && (qq % RG) == RG - 1;
+        if (refill_uv || refill_c) {
+            __syncwarp();
+            if (lane == 0) {
+                if (refill_uv) { const int gn = g0 + rr / RG + NGUV; if (gn <= glast) issue_uv(gn); }
+                if (refill_c) { const int gn = g0 + qq / RG + NGC; if (gn <= glast) issue_coef(gn); }
+            }
+        }
+    };
+
+    int r = rs;
+    const int pro_end = min(rs + T, last_tick + 1);
+    for (; r < pro_end; ++r) tick(std::true_type{}, r);          // pipeline fill (and tiny frames)
+    const int steady_end = min(H - 1, last_tick);
+    for (; r <= steady_end; ++r) tick(std::false_type{}, r);     // all T stages active, no predicates
+    for (; r <= last_tick; ++r) tick(std::true_type{}, r);       // bottom edge: virtual rows
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+template <int T> static StreamGeom geom_of() {
+    using C = typename DefaultCfg<T>::type;
+    return StreamGeom{C::HL, C::VALIDW, C::SMEM_WARP, kMaxT};
+}
+StreamGeom stream_geometry(int T) {
+    switch (T) {
+        case 1: return geom_of<1>(); case 2: return geom_of<2>(); case 3: return geom_of<3>(); case 4: return geom_of<4>();
+        case 5: return geom_of<5>(); case 6: return geom_of<6>(); case 7: return geom_of<7>(); default: return geom_of<8>();
+    }
+}
+
+template <int T, int ST> static cudaError_t prep_one() {
+    return cudaFuncSetAttribute(k_jacobi_stream<T, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+template <int T> static cudaError_t prep_T() {
+    cudaError_t e = prep_one<T, ST_CL8>();
+    if (e != cudaSuccess) return e;
+    return prep_one<T, ST_CV4>();
+}
+cudaError_t stream_prepare(int) {
+    cudaError_t e;
+    if ((e = prep_T<1>()) != cudaSuccess) return e;
+    if ((e = prep_T<2>()) != cudaSuccess) return e;
+    if ((e = prep_T<3>()) != cudaSuccess) return e;
+    if ((e = prep_T<4>()) != cudaSuccess) return e;
+    if ((e = prep_T<5>()) != cudaSuccess) return e;
+    if ((e = prep_T<6>()) != cudaSuccess) return e;
+    if ((e = prep_T<7>()) != cudaSuccess) return e;
+    return prep_T<8>();
+}
+
+template <int T, int ST>
+static cudaError_t launch_one(const CUtensorMap& tu, const CUtensorMap& tv, const CUtensorMap& ta, const CUtensorMap& tb,
+                              const CUtensorMap& tc, const StreamArgs& A, int wpc, cudaStream_t s) {
+    using C = typename DefaultCfg<T>::type;
+    const size_t smem = (size_t)wpc * C::SMEM_WARP;
+    const long long ctas = (A.total_units + wpc - 1) / wpc;
+    if (ctas <= 0) return cudaSuccess;
+    if (ctas > 0x7fffffffLL || smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    k_jacobi_stream<T, ST><<<(unsigned)ctas, wpc * 32, smem, s>>>(tu, tv, ta, tb, tc, A);
+    return cudaGetLastError();
+}
+template <int T>
+static cudaError_t launch_T(int st, const CUtensorMap& tu, const CUtensorMap& tv, const CUtensorMap& ta, const CUtensorMap& tb,
+                            const CUtensorMap& tc, const StreamArgs& A, int wpc, cudaStream_t s) {
+    return st == ST_CL8 ? launch_one<T, ST_CL8>(tu, tv, ta, tb, tc, A, wpc, s)
+                        : launch_one<T, ST_CV4>(tu, tv, ta, tb, tc, A, wpc, s);
+}
+
+cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tu, const CUtensorMap& tv, const CUtensorMap& ta,
+                                 const CUtensorMap& tb, const CUtensorMap& tc, StreamArgs A, int pairs, int wpc, cudaStream_t s) {
+    const StreamGeom G = stream_geometry(T);
+    const int rows = A.out_hi - A.out_lo;
+    if (rows <= 0 || pairs <= 0) return cudaSuccess;
+    A.nsx = (A.W + G.valid_w - 1) / G.valid_w;
+    A.ncy = (rows + A.chunk_rows - 1) / A.chunk_rows;
+    A.total_units = (long long)A.nsx * A.ncy * pairs;
+    if (wpc < 1) wpc = 1;
+    if (wpc > 8) wpc = 8;
+    while (wpc > 1 && (size_t)wpc * G.smem_per_warp > 227 * 1024) --wpc;
+    switch (T) {
+        case 1: return launch_T<1>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        case 2: return launch_T<2>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        case 3: return launch_T<3>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        case 4: return launch_T<4>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        case 5: return launch_T<5>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        case 6: return launch_T<6>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        case 7: return launch_T<7>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        case 8: return launch_T<8>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace hs

@@ -1,0 +1,705 @@
+// hsflow_capi.cu -- the C ABI of libhsflow.so (declared in include/hsflow.h).
+//
+// Host orchestration of the Horn-Schunck path, replacing HSOpticalFlowOpenCL::setupCL /
+// runDerivatives / runCLKernels / cleanup (HSOpticalFlowOpenCL.cpp:67-679, 849-892): device
+// planes live in HBM for the whole computation (no per-iteration PCIe round trip, cpp:483-501,
+// 655-675), scalar fp32 planes instead of float4 (4 B/px instead of 16 B/px), one CUDA stream
+// per handle, TMA descriptors built once per geometry.  No CPU fallback of any kind.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/hsflow.h"
+#include "hs_common.cuh"
+#include "hs_launch.h"
+
+using namespace hs;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(HSFLOW_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define NEED(h) do { if (!(h)) return fail(HSFLOW_EINVAL, "null handle"); } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct hsflow {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, s_in = nullptr, s_out = nullptr;
+    EncodeTiledFn encode = nullptr;
+    int sm_count = 148;
+    // parameters (defaults = main.cpp:4-8: ALPHA "15", ITERATIONS "100", LAMBDA ".1")
+    float alpha = 15.f, lambda = 0.1f, rho = 225.f;
+    int iterations = 100, stencil = HSFLOW_STENCIL_CL8, update_v = 1, tblock = 0;
+    int math = HSFLOW_MATH_FAST, deriv = HSFLOW_DERIV_CL, kernel_sel = 0;
+    int chunk_rows = 0, wpc = 0, sub_batch = 0, warm = 0;
+    // geometry
+    int W = 0, H = 0, P = 0, S = 0;
+    int fmt = -1;
+    long long f_row_pitch = 0, f_pair_pitch = 0;   // bytes
+    long long pitch = 0, ppair = 0;                // elements
+    int top_edge = 1, bottom_edge = 1;
+    // device memory
+    uint8_t *f1 = nullptr, *f2 = nullptr, *fb1 = nullptr, *fb2 = nullptr;
+    float *uA = nullptr, *vA = nullptr, *uB = nullptr, *vB = nullptr, *c0 = nullptr, *c1 = nullptr, *c2 = nullptr;
+    float* dtmp = nullptr;                         // 3 planes of one pair, for hsflow_read_derivatives
+    uint8_t* d_mask = nullptr;
+    int* d_count = nullptr;
+    size_t mask_cap = 0;
+    CUtensorMap tm_uA, tm_vA, tm_uB, tm_vB, tm_c0, tm_c1, tm_c2;
+    // state
+    int cur = 0;                                   // 0: uA/vA hold the current field, 1: uB/vB
+    int valid_lo = 0, valid_hi = 0;
+    int prepared = 0, coef_norm = -1;
+    cudaEvent_t ev0[4] = {}, ev1[4] = {};
+    int ev_set[4] = {};
+    long long launches = 0;
+};
+
+static void free_planes(hsflow* h) {
+    cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2);
+    cudaFree(h->uA); cudaFree(h->vA); cudaFree(h->uB); cudaFree(h->vB);
+    cudaFree(h->c0); cudaFree(h->c1); cudaFree(h->c2); cudaFree(h->dtmp);
+    h->f1 = h->f2 = h->fb1 = h->fb2 = nullptr;
+    h->uA = h->vA = h->uB = h->vB = h->c0 = h->c1 = h->c2 = h->dtmp = nullptr;
+    h->fmt = -1;
+    h->prepared = 0;
+}
+
+static int effective_T(const hsflow* h) {
+    if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1) return 1;
+    int T = h->tblock > 0 ? h->tblock : 4;
+    return std::min(T, kMaxT);
+}
+static bool use_stream_kernel(const hsflow* h, int t) {
+    if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1) return false;
+    return t >= 2 || h->kernel_sel == 2;
+}
+
+static int make_map(hsflow* h, CUtensorMap* tm, float* base, int pairs) {
+    cuuint64_t dims[3] = {(cuuint64_t)h->W, (cuuint64_t)h->H, (cuuint64_t)pairs};
+    cuuint64_t strides[2] = {(cuuint64_t)h->pitch * 4, (cuuint64_t)h->ppair * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kStripW, (cuuint32_t)kStreamRowsPerBox, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HSFLOW_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return HSFLOW_OK;
+}
+
+static void phase_begin(hsflow* h, int ph) { cudaEventRecord(h->ev0[ph], h->stream); }
+static void phase_end(hsflow* h, int ph) { cudaEventRecord(h->ev1[ph], h->stream); h->ev_set[ph] = 1; }
+
+extern "C" {
+
+const char* hsflow_last_error(void) { return g_err; }
+int hsflow_version(void) { return 100; }
+int hsflow_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hsflow_create(int device, hsflow_t** out) {
+    if (!out) return fail(HSFLOW_EINVAL, "out is null");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(HSFLOW_ENODEV, "no CUDA device: libhsflow has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(HSFLOW_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(HSFLOW_ENODEV, "device %d is sm_%d%d; libhsflow is built for sm_100a only", device, prop.major, prop.minor);
+    hsflow* h = new (std::nothrow) hsflow();
+    if (!h) return fail(HSFLOW_ENOMEM, "out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        delete h;
+        return fail(HSFLOW_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    }
+    h->encode = (EncodeTiledFn)fn;
+    e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(HSFLOW_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    h->stream = h->own_stream;
+    for (int i = 0; i < 4; ++i) { cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]); }
+    e = stream_prepare(device);
+    if (e != cudaSuccess) { hsflow_destroy(h); return fail(HSFLOW_ECUDA, "kernel attribute setup: %s", cudaGetErrorString(e)); }
+    if (cudaMalloc(&h->d_count, sizeof(int)) != cudaSuccess) { hsflow_destroy(h); return fail(HSFLOW_ENOMEM, "cudaMalloc"); }
+    *out = h;
+    return HSFLOW_OK;
+}
+
+int hsflow_destroy(hsflow_t* h) {
+    if (!h) return HSFLOW_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_planes(h);
+    cudaFree(h->d_mask); cudaFree(h->d_count);
+    for (int i = 0; i < 4; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    delete h;
+    return HSFLOW_OK;
+}
+
+int hsflow_set_stream(hsflow_t* h, void* s) {
+    NEED(h);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return HSFLOW_OK;
+}
+
+int hsflow_set_params(hsflow_t* h, float alpha, int iterations, int stencil, int update_v, int temporal_block) {
+    NEED(h);
+    if (iterations < 0) return fail(HSFLOW_EINVAL, "iterations must be >= 0");
+    if (stencil != HSFLOW_STENCIL_CL8 && stencil != HSFLOW_STENCIL_CV4) return fail(HSFLOW_EINVAL, "unknown stencil %d", stencil);
+    if (temporal_block < 0 || temporal_block > kMaxT) return fail(HSFLOW_EINVAL, "temporal_block must be 0..%d", kMaxT);
+    h->alpha = alpha;
+    h->rho = alpha * alpha;                        // Kernels.cl:85 alpha*alpha, in float
+    h->iterations = iterations;
+    h->stencil = stencil;
+    h->update_v = update_v ? 1 : 0;
+    h->tblock = temporal_block;
+    h->prepared = 0;
+    return HSFLOW_OK;
+}
+int hsflow_set_lambda(hsflow_t* h, float lambda) {
+    NEED(h);
+    if (!(lambda > 0.f)) return fail(HSFLOW_EINVAL, "lambda must be > 0");
+    h->lambda = lambda;
+    h->rho = 1.0f / lambda;                        // cvCalcOpticalFlowHS: rho = 1/lambda
+    h->prepared = 0;
+    return HSFLOW_OK;
+}
+int hsflow_set_math(hsflow_t* h, int m) {
+    NEED(h);
+    if (m != HSFLOW_MATH_FAST && m != HSFLOW_MATH_EXACT) return fail(HSFLOW_EINVAL, "unknown math mode %d", m);
+    h->math = m; h->prepared = 0;
+    return HSFLOW_OK;
+}
+int hsflow_set_deriv(hsflow_t* h, int d) {
+    NEED(h);
+    if (d != HSFLOW_DERIV_CL && d != HSFLOW_DERIV_CV) return fail(HSFLOW_EINVAL, "unknown derivative mode %d", d);
+    h->deriv = d; h->prepared = 0;
+    return HSFLOW_OK;
+}
+int hsflow_set_tuning(hsflow_t* h, int chunk_rows, int warps_per_cta, int sub_batch) {
+    NEED(h);
+    if (chunk_rows < 0 || warps_per_cta < 0 || warps_per_cta > 8 || sub_batch < 0) return fail(HSFLOW_EINVAL, "bad tuning value");
+    h->chunk_rows = chunk_rows; h->wpc = warps_per_cta;
+    if (sub_batch != h->sub_batch && h->P > 0) return fail(HSFLOW_EINVAL, "sub_batch must be set before hsflow_configure");
+    h->sub_batch = sub_batch;
+    return HSFLOW_OK;
+}
+int hsflow_set_kernel(hsflow_t* h, int which) {   /* 0 auto, 1 single-sweep kernel only, 2 streaming kernel even for T = 1 */
+    NEED(h);
+    if (which < 0 || which > 2) return fail(HSFLOW_EINVAL, "kernel selector 0..2");
+    h->kernel_sel = which;
+    return HSFLOW_OK;
+}
+int hsflow_set_warm_start(hsflow_t* h, int keep) { NEED(h); h->warm = keep ? 1 : 0; return HSFLOW_OK; }
+
+int hsflow_configure(hsflow_t* h, int W, int H, int P) {
+    NEED(h);
+    if (W <= 0 || H <= 0 || P <= 0) return fail(HSFLOW_EINVAL, "width, height, pairs must be positive");
+    if (W > (1 << 24) || H > (1 << 24)) return fail(HSFLOW_EINVAL, "frame too large");
+    CK(cudaSetDevice(h->device));
+    if (h->W == W && h->H == H && h->P == P && h->uA) { h->prepared = 0; h->top_edge = h->bottom_edge = 1; return HSFLOW_OK; }
+    CK(cudaStreamSynchronize(h->stream));
+    free_planes(h);
+    h->W = W; h->H = H; h->P = P;
+    h->S = h->sub_batch > 0 ? std::min(h->sub_batch, P) : std::min(P, 32);
+    h->pitch = ((long long)W + 31) / 32 * 32;
+    h->ppair = h->pitch * H;
+    h->top_edge = h->bottom_edge = 1;
+    const size_t planeP = (size_t)h->ppair * P * sizeof(float), planeS = (size_t)h->ppair * h->S * sizeof(float);
+    if (cudaMalloc(&h->uA, planeP) != cudaSuccess || cudaMalloc(&h->vA, planeP) != cudaSuccess ||
+        cudaMalloc(&h->uB, planeS) != cudaSuccess || cudaMalloc(&h->vB, planeS) != cudaSuccess ||
+        cudaMalloc(&h->c0, planeS) != cudaSuccess || cudaMalloc(&h->c1, planeS) != cudaSuccess ||
+        cudaMalloc(&h->c2, planeS) != cudaSuccess) {
+        cudaGetLastError();
+        free_planes(h);
+        h->W = h->H = h->P = 0;
+        return fail(HSFLOW_ENOMEM, "cudaMalloc of %d x %d x %d planes failed", W, H, P);
+    }
+    int rc;
+    if ((rc = make_map(h, &h->tm_uA, h->uA, P)) || (rc = make_map(h, &h->tm_vA, h->vA, P)) ||
+        (rc = make_map(h, &h->tm_uB, h->uB, h->S)) || (rc = make_map(h, &h->tm_vB, h->vB, h->S)) ||
+        (rc = make_map(h, &h->tm_c0, h->c0, h->S)) || (rc = make_map(h, &h->tm_c1, h->c1, h->S)) ||
+        (rc = make_map(h, &h->tm_c2, h->c2, h->S)))
+        return rc;
+    CK(cudaMemsetAsync(h->uA, 0, planeP, h->stream));
+    CK(cudaMemsetAsync(h->vA, 0, planeP, h->stream));
+    h->cur = 0; h->valid_lo = 0; h->valid_hi = H;
+    return HSFLOW_OK;
+}
+
+int hsflow_set_strip(hsflow_t* h, int top, int bottom) {
+    NEED(h);
+    h->top_edge = top ? 1 : 0; h->bottom_edge = bottom ? 1 : 0;
+    return HSFLOW_OK;
+}
+
+static int ensure_frames(hsflow* h, int fmt) {
+    if (h->P <= 0) return fail(HSFLOW_EINVAL, "hsflow_configure first");
+    if (h->fmt == fmt && h->f1) return HSFLOW_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2);
+    h->f1 = h->f2 = h->fb1 = h->fb2 = nullptr;
+    const int bpp = fmt == FMT_GRAY8 ? 1 : (fmt == FMT_BGR8 ? 3 : 4);
+    h->f_row_pitch = ((long long)h->W * bpp + 16 + 127) / 128 * 128;   // +16: vector loads may overrun the last pixel
+    h->f_pair_pitch = h->f_row_pitch * h->H;
+    const size_t bytes = (size_t)h->f_pair_pitch * h->P;
+    if (cudaMalloc(&h->f1, bytes) != cudaSuccess || cudaMalloc(&h->f2, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HSFLOW_ENOMEM, "cudaMalloc of frame planes failed");
+    }
+    CK(cudaMemsetAsync(h->f1, 0, bytes, h->stream));
+    CK(cudaMemsetAsync(h->f2, 0, bytes, h->stream));
+    h->fmt = fmt;
+    return HSFLOW_OK;
+}
+
+static int set_frames(hsflow* h, int fmt, int pair, const void* a, const void* b, size_t pitch, cudaMemcpyKind kind) {
+    NEED(h);
+    if (!a || !b) return fail(HSFLOW_EINVAL, "null frame pointer");
+    if (pair < 0 || pair >= h->P) return fail(HSFLOW_EINVAL, "pair %d out of range (configured %d)", pair, h->P);
+    int rc = ensure_frames(h, fmt);
+    if (rc) return rc;
+    const int bpp = fmt == FMT_GRAY8 ? 1 : (fmt == FMT_BGR8 ? 3 : 4);
+    const size_t wbytes = (size_t)h->W * bpp;
+    if (pitch == 0) pitch = wbytes;
+    if (pitch < wbytes) return fail(HSFLOW_EINVAL, "pitch %zu smaller than a row (%zu bytes)", pitch, wbytes);
+    phase_begin(h, HSFLOW_PHASE_LOAD);
+    CK(cudaMemcpy2DAsync(h->f1 + (size_t)pair * h->f_pair_pitch, h->f_row_pitch, a, pitch, wbytes, h->H, kind, h->stream));
+    CK(cudaMemcpy2DAsync(h->f2 + (size_t)pair * h->f_pair_pitch, h->f_row_pitch, b, pitch, wbytes, h->H, kind, h->stream));
+    phase_end(h, HSFLOW_PHASE_LOAD);
+    h->prepared = 0;
+    return HSFLOW_OK;
+}
+int hsflow_set_frames_gray8(hsflow_t* h, int pair, const uint8_t* f1, const uint8_t* f2, size_t pitch) {
+    return set_frames(h, FMT_GRAY8, pair, f1, f2, pitch, cudaMemcpyHostToDevice);
+}
+int hsflow_set_frames_bgr8(hsflow_t* h, int pair, const uint8_t* f1, const uint8_t* f2, size_t pitch) {
+    return set_frames(h, FMT_BGR8, pair, f1, f2, pitch, cudaMemcpyHostToDevice);
+}
+int hsflow_set_frames_f32(hsflow_t* h, int pair, const float* f1, const float* f2, size_t pitch) {
+    return set_frames(h, FMT_F32, pair, f1, f2, pitch, cudaMemcpyHostToDevice);
+}
+int hsflow_set_frames_gray8_dev(hsflow_t* h, int pair, const uint8_t* f1, const uint8_t* f2, size_t pitch) {
+    return set_frames(h, FMT_GRAY8, pair, f1, f2, pitch, cudaMemcpyDeviceToDevice);
+}
+int hsflow_synth_frames(hsflow_t* h, int full_height, int row0, uint32_t seed0) {
+    NEED(h);
+    int rc = ensure_frames(h, FMT_GRAY8);
+    if (rc) return rc;
+    if (full_height <= 0) full_height = h->H;
+    CK(launch_synth(h->f1, h->f2, h->W, h->H, full_height, row0, h->f_row_pitch, h->f_pair_pitch, seed0, h->P, h->stream));
+    h->launches++;
+    h->prepared = 0;
+    return HSFLOW_OK;
+}
+int hsflow_load_pair_gray8(hsflow_t* h, const uint8_t* f1, const uint8_t* f2, int w, int hgt, size_t pitch) {
+    int rc = hsflow_configure(h, w, hgt, 1);
+    return rc ? rc : hsflow_set_frames_gray8(h, 0, f1, f2, pitch);
+}
+int hsflow_load_pair_bgr8(hsflow_t* h, const uint8_t* f1, const uint8_t* f2, int w, int hgt, size_t pitch) {
+    int rc = hsflow_configure(h, w, hgt, 1);
+    return rc ? rc : hsflow_set_frames_bgr8(h, 0, f1, f2, pitch);
+}
+int hsflow_load_pair_f32(hsflow_t* h, const float* f1, const float* f2, int w, int hgt, size_t pitch) {
+    int rc = hsflow_configure(h, w, hgt, 1);
+    return rc ? rc : hsflow_set_frames_f32(h, 0, f1, f2, pitch);
+}
+
+// derivatives of pairs [p0, p0+n) into coefficient slots [0, n)
+static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* o1, float* o2) {
+    DerivArgs A;
+    A.f_row_pitch = h->f_row_pitch; A.f_pair_pitch = h->f_pair_pitch;
+    A.c0 = o0; A.c1 = o1; A.c2 = o2;
+    A.c_row_pitch = h->pitch; A.c_pair_pitch = h->ppair;
+    A.W = h->W; A.H = h->H; A.normalise = normalise; A.rho = h->rho;
+    if (h->deriv == HSFLOW_DERIV_CL) {
+        A.f1 = h->f1 + (size_t)p0 * h->f_pair_pitch;
+        A.f2 = h->f2 + (size_t)p0 * h->f_pair_pitch;
+        CK(launch_deriv(A, h->fmt, n, h->stream));
+        h->launches++;
+    } else {
+        if (h->fmt != FMT_GRAY8) return fail(HSFLOW_EINVAL, "HSFLOW_DERIV_CV needs gray8 frames");
+        if (!h->top_edge || !h->bottom_edge) return fail(HSFLOW_EINVAL, "HSFLOW_DERIV_CV is not available in strip mode");
+        if (!h->fb1) {
+            const size_t bytes = (size_t)h->f_pair_pitch * h->S;
+            if (cudaMalloc(&h->fb1, bytes) != cudaSuccess || cudaMalloc(&h->fb2, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(HSFLOW_ENOMEM, "cudaMalloc of blur planes failed");
+            }
+        }
+        CK(launch_box3(h->f1 + (size_t)p0 * h->f_pair_pitch, h->fb1, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
+        CK(launch_box3(h->f2 + (size_t)p0 * h->f_pair_pitch, h->fb2, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
+        A.f1 = h->fb1; A.f2 = h->fb2;
+        CK(launch_deriv_cv(A, n, h->stream));
+        h->launches += 3;
+    }
+    return HSFLOW_OK;
+}
+
+static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T) {
+    if (h->chunk_rows > 0) return std::min(h->chunk_rows, rows);
+    // aim at >= ~16 work units per resident warp slot, chunks of at least 16*T rows
+    const long long slots = (long long)h->sm_count * 10;
+    const long long per_row_units = (long long)nsx * pairs;
+    long long want_chunks = (slots * 16 + per_row_units - 1) / per_row_units;
+    long long ch = rows / std::max<long long>(want_chunks, 1);
+    ch = std::max<long long>(ch, 16LL * T);
+    ch = std::min<long long>(ch, rows);
+    return (int)std::max<long long>(ch, 1);
+}
+
+// one launch advancing t iterations for n pairs.  src/dst: 0 = A planes (pair offset pA), 1 = B planes (offset 0)
+static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int out_hi) {
+    float* uo = src == 0 ? h->uB : h->uA + (size_t)pA * h->ppair;
+    float* vo = src == 0 ? h->vB : h->vA + (size_t)pA * h->ppair;
+    if (use_stream_kernel(h, t)) {
+        StreamArgs A;
+        memset(&A, 0, sizeof A);
+        A.u_out = uo; A.v_out = vo;
+        A.row_pitch = h->pitch; A.out_pair_pitch = h->ppair;
+        A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
+        const StreamGeom G = stream_geometry(t);
+        const int nsx = (h->W + G.valid_w - 1) / G.valid_w;
+        A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, nsx, n, t);
+        A.z_in0 = src == 0 ? pA : 0;
+        A.z_c0 = 0;
+        const int wpc = h->wpc > 0 ? h->wpc : 4;
+        CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uA : h->tm_uB, src == 0 ? h->tm_vA : h->tm_vB,
+                                h->tm_c0, h->tm_c1, h->tm_c2, A, n, wpc, h->stream));
+        h->launches++;
+        return HSFLOW_OK;
+    }
+    if (t != 1) return fail(HSFLOW_EINVAL, "internal: single-sweep kernel advances one iteration per launch");
+    Jacobi1Args A;
+    memset(&A, 0, sizeof A);
+    A.u_in = src == 0 ? h->uA + (size_t)pA * h->ppair : h->uB;
+    A.v_in = src == 0 ? h->vA + (size_t)pA * h->ppair : h->vB;
+    A.u_out = uo; A.v_out = vo;
+    A.c0 = h->c0; A.c1 = h->c1; A.c2 = h->c2;
+    A.row_pitch = h->pitch; A.in_pair_pitch = A.out_pair_pitch = A.c_pair_pitch = h->ppair;
+    A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
+    A.chunk_rows = h->chunk_rows > 0 ? h->chunk_rows : std::max(1, std::min(out_hi - out_lo, 64));
+    A.rho = h->rho;
+    CK(launch_jacobi1(A, h->math == HSFLOW_MATH_EXACT, h->stencil, h->update_v != 0, n, h->stream));
+    h->launches++;
+    return HSFLOW_OK;
+}
+
+int hsflow_prepare(hsflow_t* h) {
+    NEED(h);
+    if (h->P <= 0 || !h->f1) return fail(HSFLOW_EINVAL, "configure and load frames first");
+    if (h->P > h->S) return fail(HSFLOW_EINVAL, "hsflow_prepare/iterate need pairs <= sub_batch (%d > %d); use hsflow_compute", h->P, h->S);
+    CK(cudaSetDevice(h->device));
+    phase_begin(h, HSFLOW_PHASE_DERIV);
+    const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
+    int rc = run_deriv(h, 0, h->P, norm, h->c0, h->c1, h->c2);
+    if (rc) return rc;
+    h->coef_norm = norm;
+    if (!h->warm) {                                // cpp:331-332: u, v start at zero for every pair
+        float* u = h->cur == 0 ? h->uA : h->uB;
+        float* v = h->cur == 0 ? h->vA : h->vB;
+        CK(cudaMemsetAsync(u, 0, (size_t)h->ppair * h->P * sizeof(float), h->stream));
+        CK(cudaMemsetAsync(v, 0, (size_t)h->ppair * h->P * sizeof(float), h->stream));
+    }
+    phase_end(h, HSFLOW_PHASE_DERIV);
+    h->valid_lo = 0; h->valid_hi = h->H;
+    h->prepared = 1;
+    return HSFLOW_OK;
+}
+
+int hsflow_iterate(hsflow_t* h, int n) {
+    NEED(h);
+    if (!h->prepared) return fail(HSFLOW_EINVAL, "hsflow_prepare first");
+    if (n < 0) return fail(HSFLOW_EINVAL, "n must be >= 0");
+    CK(cudaSetDevice(h->device));
+    const int T = effective_T(h);
+    phase_begin(h, HSFLOW_PHASE_ITER);
+    while (n > 0) {
+        const int t = std::min(n, T);
+        const int lo = h->top_edge ? 0 : h->valid_lo + t;
+        const int hi = h->bottom_edge ? h->H : h->valid_hi - t;
+        if (lo >= hi) return fail(HSFLOW_EINVAL, "ghost rows exhausted: refresh the halo (valid rows [%d,%d), block %d)", h->valid_lo, h->valid_hi, t);
+        // the single-sweep path ping-pongs internally; keep the bookkeeping identical for both
+        if (use_stream_kernel(h, t)) {
+            int rc = run_block(h, t, h->cur, 0, h->P, lo, hi);
+            if (rc) return rc;
+            h->cur ^= 1;
+        } else {
+            for (int k = 0; k < t; ++k) {
+                const int lo1 = h->top_edge ? 0 : h->valid_lo + k + 1;
+                const int hi1 = h->bottom_edge ? h->H : h->valid_hi - k - 1;
+                int rc = run_block(h, 1, h->cur, 0, h->P, lo1, hi1);
+                if (rc) return rc;
+                h->cur ^= 1;
+            }
+        }
+        h->valid_lo = lo; h->valid_hi = hi;
+        n -= t;
+    }
+    phase_end(h, HSFLOW_PHASE_ITER);
+    return HSFLOW_OK;
+}
+
+int hsflow_halo_refreshed(hsflow_t* h) { NEED(h); h->valid_lo = 0; h->valid_hi = h->H; return HSFLOW_OK; }
+
+// derivative pass + all iterations for pairs [p0, p0+n) (n <= S); the result lands in the A planes
+static int compute_subbatch(hsflow* h, int p0, int n) {
+    const int T = effective_T(h), N = h->iterations;
+    const bool streamk = use_stream_kernel(h, std::min(T, std::max(N, 1)));
+    int L = 0;                                     // ping-pong flips
+    for (int left = N; left > 0;) { const int t = std::min(left, T); L += use_stream_kernel(h, t) ? 1 : t; left -= t; }
+    (void)streamk;
+    const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
+    int rc = run_deriv(h, p0, n, norm, h->c0, h->c1, h->c2);
+    if (rc) return rc;
+    h->coef_norm = norm;
+    int src = (L % 2 == 0) ? 0 : 1;                // so that the last flip lands in A
+    float* u = src == 0 ? h->uA + (size_t)p0 * h->ppair : h->uB;
+    float* v = src == 0 ? h->vA + (size_t)p0 * h->ppair : h->vB;
+    CK(cudaMemsetAsync(u, 0, (size_t)h->ppair * n * sizeof(float), h->stream));   // cpp:331-332
+    CK(cudaMemsetAsync(v, 0, (size_t)h->ppair * n * sizeof(float), h->stream));
+    for (int left = N; left > 0;) {
+        const int t = std::min(left, T);
+        if (use_stream_kernel(h, t)) {
+            rc = run_block(h, t, src, p0, n, 0, h->H);
+            if (rc) return rc;
+            src ^= 1;
+        } else {
+            for (int k = 0; k < t; ++k) { rc = run_block(h, 1, src, p0, n, 0, h->H); if (rc) return rc; src ^= 1; }
+        }
+        left -= t;
+    }
+    if (src != 0) return fail(HSFLOW_ECUDA, "internal: sub-batch result not in the output planes");
+    return HSFLOW_OK;
+}
+
+int hsflow_compute(hsflow_t* h) {
+    NEED(h);
+    if (h->P <= 0 || !h->f1) return fail(HSFLOW_EINVAL, "configure and load frames first");
+    if (h->P <= h->S) {
+        int rc = hsflow_prepare(h);
+        return rc ? rc : hsflow_iterate(h, h->iterations);
+    }
+    // batch larger than the scratch: sub-batches of S pairs; results always end in the A planes
+    if (h->warm) return fail(HSFLOW_EINVAL, "warm start needs pairs <= sub_batch");
+    CK(cudaSetDevice(h->device));
+    phase_begin(h, HSFLOW_PHASE_ITER);
+    for (int p0 = 0; p0 < h->P; p0 += h->S) {
+        int rc = compute_subbatch(h, p0, std::min(h->S, h->P - p0));
+        if (rc) return rc;
+    }
+    phase_end(h, HSFLOW_PHASE_ITER);
+    h->cur = 0;
+    h->prepared = 0;
+    return HSFLOW_OK;
+}
+
+int hsflow_sync(hsflow_t* h) {
+    NEED(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return HSFLOW_OK;
+}
+
+static float* cur_u(hsflow* h) { return h->cur == 0 ? h->uA : h->uB; }
+static float* cur_v(hsflow* h) { return h->cur == 0 ? h->vA : h->vB; }
+
+int hsflow_read_uv(hsflow_t* h, int pair, float* u, float* v, size_t pitch) {
+    NEED(h);
+    if (pair < 0 || pair >= h->P) return fail(HSFLOW_EINVAL, "pair %d out of range", pair);
+    if (h->cur == 1 && pair >= h->S) return fail(HSFLOW_EINVAL, "internal: pair outside scratch planes");
+    const size_t wb = (size_t)h->W * sizeof(float);
+    if (pitch == 0) pitch = wb;
+    if (pitch < wb) return fail(HSFLOW_EINVAL, "pitch too small");
+    phase_begin(h, HSFLOW_PHASE_READ);
+    if (u) CK(cudaMemcpy2DAsync(u, pitch, cur_u(h) + (size_t)pair * h->ppair, h->pitch * sizeof(float), wb, h->H, cudaMemcpyDeviceToHost, h->stream));
+    if (v) CK(cudaMemcpy2DAsync(v, pitch, cur_v(h) + (size_t)pair * h->ppair, h->pitch * sizeof(float), wb, h->H, cudaMemcpyDeviceToHost, h->stream));
+    phase_end(h, HSFLOW_PHASE_READ);
+    CK(cudaStreamSynchronize(h->stream));
+    return HSFLOW_OK;
+}
+
+int hsflow_write_uv(hsflow_t* h, int pair, const float* u, const float* v, size_t pitch) {
+    NEED(h);
+    if (pair < 0 || pair >= h->P || (h->cur == 1 && pair >= h->S)) return fail(HSFLOW_EINVAL, "pair %d out of range", pair);
+    const size_t wb = (size_t)h->W * sizeof(float);
+    if (pitch == 0) pitch = wb;
+    if (u) CK(cudaMemcpy2DAsync(cur_u(h) + (size_t)pair * h->ppair, h->pitch * sizeof(float), u, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
+    if (v) CK(cudaMemcpy2DAsync(cur_v(h) + (size_t)pair * h->ppair, h->pitch * sizeof(float), v, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return HSFLOW_OK;
+}
+
+int hsflow_read_derivatives(hsflow_t* h, int pair, float* Ex, float* Ey, float* Et, size_t pitch) {
+    NEED(h);
+    if (pair < 0 || pair >= h->P || !h->f1) return fail(HSFLOW_EINVAL, "pair %d out of range or no frames", pair);
+    const size_t wb = (size_t)h->W * sizeof(float);
+    if (pitch == 0) pitch = wb;
+    if (!h->dtmp && cudaMalloc(&h->dtmp, 3 * (size_t)h->ppair * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HSFLOW_ENOMEM, "cudaMalloc");
+    }
+    float* d[3] = {h->dtmp, h->dtmp + h->ppair, h->dtmp + 2 * h->ppair};
+    int rc = run_deriv(h, pair, 1, 0, d[0], d[1], d[2]);
+    if (rc) return rc;
+    float* o[3] = {Ex, Ey, Et};
+    for (int k = 0; k < 3; ++k)
+        if (o[k]) CK(cudaMemcpy2DAsync(o[k], pitch, d[k], h->pitch * sizeof(float), wb, h->H, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return HSFLOW_OK;
+}
+
+int hsflow_get_device_uv(hsflow_t* h, float** u, float** v, size_t* row_pitch, size_t* pair_pitch) {
+    NEED(h);
+    if (!h->uA) return fail(HSFLOW_EINVAL, "not configured");
+    if (u) *u = cur_u(h);
+    if (v) *v = cur_v(h);
+    if (row_pitch) *row_pitch = (size_t)h->pitch;
+    if (pair_pitch) *pair_pitch = (size_t)h->ppair;
+    return HSFLOW_OK;
+}
+int hsflow_get_device_frames(hsflow_t* h, uint8_t** f1, uint8_t** f2, size_t* row_pitch, size_t* pair_pitch) {
+    NEED(h);
+    int rc = ensure_frames(h, h->fmt >= 0 ? h->fmt : FMT_GRAY8);
+    if (rc) return rc;
+    if (f1) *f1 = h->f1;
+    if (f2) *f2 = h->f2;
+    if (row_pitch) *row_pitch = (size_t)h->f_row_pitch;
+    if (pair_pitch) *pair_pitch = (size_t)h->f_pair_pitch;
+    return HSFLOW_OK;
+}
+
+int hsflow_dot_mask(hsflow_t* h, int pair, int step, float thr, uint8_t* mask, int* count) {
+    NEED(h);
+    if (pair < 0 || pair >= h->P || step <= 0 || !mask) return fail(HSFLOW_EINVAL, "bad argument");
+    if (h->cur == 1 && pair >= h->S) return fail(HSFLOW_EINVAL, "internal: pair outside scratch planes");
+    const int gw = (h->W + step - 1) / step, gh = (h->H + step - 1) / step;
+    const size_t need = (size_t)gw * gh;
+    if (need > h->mask_cap) {
+        cudaFree(h->d_mask); h->d_mask = nullptr; h->mask_cap = 0;
+        if (cudaMalloc(&h->d_mask, need) != cudaSuccess) { cudaGetLastError(); return fail(HSFLOW_ENOMEM, "cudaMalloc"); }
+        h->mask_cap = need;
+    }
+    CK(cudaMemsetAsync(h->d_count, 0, sizeof(int), h->stream));
+    CK(launch_dot_mask(cur_u(h) + (size_t)pair * h->ppair, cur_v(h) + (size_t)pair * h->ppair, h->W, h->H, h->pitch, step, thr,
+                       h->d_mask, h->d_count, h->stream));
+    h->launches++;
+    CK(cudaMemcpyAsync(mask, h->d_mask, need, cudaMemcpyDeviceToHost, h->stream));
+    int c = 0;
+    CK(cudaMemcpyAsync(&c, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (count) *count = c;
+    return HSFLOW_OK;
+}
+
+int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out) {
+    NEED(h);
+    if (!frames || !u_out || !v_out || n_pairs <= 0) return fail(HSFLOW_EINVAL, "bad argument");
+    if (!h->top_edge || !h->bottom_edge) return fail(HSFLOW_EINVAL, "not available in strip mode");
+    const long long px = (long long)w * hgt;
+    int B = (int)std::max<long long>(1, std::min<long long>(16, (32LL << 20) / std::max<long long>(px, 1)));
+    B = std::min(B, n_pairs);
+    const int K = 3;                               // sub-batches in flight: H2D | compute | D2H
+    if (!(h->W == w && h->H == hgt && h->P == K * B && h->S == B)) {
+        const int keep = h->sub_batch;
+        CK(cudaStreamSynchronize(h->stream));
+        free_planes(h); h->W = h->H = h->P = 0;
+        h->sub_batch = B;
+        int rc = hsflow_configure(h, w, hgt, K * B);
+        h->sub_batch = keep;
+        if (rc) return rc;
+    }
+    int rc = ensure_frames(h, FMT_GRAY8);
+    if (rc) return rc;
+    if (!h->s_in) { CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)); }
+    cudaEvent_t ev_in[K], ev_comp[K], ev_out[K];
+    for (int k = 0; k < K; ++k) {
+        CK(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_comp[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+    }
+    // order the side streams after whatever the handle's stream did so far (allocation memsets)
+    CK(cudaEventRecord(ev_comp[0], h->stream));
+    CK(cudaStreamWaitEvent(h->s_in, ev_comp[0], 0));
+    const size_t fbytes = (size_t)px, wb = (size_t)w * sizeof(float);
+    const int nsb = (n_pairs + B - 1) / B;
+    int status = HSFLOW_OK;
+    for (int i = 0; i < nsb && status == HSFLOW_OK; ++i) {
+        const int slot = i % K, p0 = slot * B, first = i * B, n = std::min(B, n_pairs - first);
+        if (i >= K) CK(cudaStreamWaitEvent(h->s_in, ev_comp[slot], 0));      // frames of the slot were consumed
+        for (int k = 0; k < n; ++k) {
+            const uint8_t* src = frames + (size_t)(first + k) * 2 * fbytes;
+            CK(cudaMemcpy2DAsync(h->f1 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src, w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
+            CK(cudaMemcpy2DAsync(h->f2 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src + fbytes, w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
+        }
+        CK(cudaEventRecord(ev_in[slot], h->s_in));
+        CK(cudaStreamWaitEvent(h->stream, ev_in[slot], 0));
+        if (i >= K) CK(cudaStreamWaitEvent(h->stream, ev_out[slot], 0));     // u/v of the slot were read back
+        status = compute_subbatch(h, p0, n);
+        if (status) break;
+        CK(cudaEventRecord(ev_comp[slot], h->stream));
+        CK(cudaStreamWaitEvent(h->s_out, ev_comp[slot], 0));
+        for (int k = 0; k < n; ++k) {
+            CK(cudaMemcpy2DAsync(u_out + (size_t)(first + k) * px, wb, h->uA + (size_t)(p0 + k) * h->ppair, h->pitch * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
+            CK(cudaMemcpy2DAsync(v_out + (size_t)(first + k) * px, wb, h->vA + (size_t)(p0 + k) * h->ppair, h->pitch * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
+        }
+        CK(cudaEventRecord(ev_out[slot], h->s_out));
+    }
+    cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->s_out);
+    for (int k = 0; k < K; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_comp[k]); cudaEventDestroy(ev_out[k]); }
+    h->cur = 0; h->prepared = 0;
+    if (status) return status;
+    CK(cudaGetLastError());
+    return HSFLOW_OK;
+}
+
+float hsflow_last_ms(hsflow_t* h, int phase) {
+    if (!h || phase < 0 || phase > 3 || !h->ev_set[phase]) return -1.f;
+    if (cudaEventSynchronize(h->ev1[phase]) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0[phase], h->ev1[phase]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    return ms;
+}
+long long hsflow_kernel_launches(hsflow_t* h) { return h ? h->launches : 0; }
+int hsflow_effective_temporal_block(hsflow_t* h) { return h ? effective_T(h) : 0; }
+
+void* hsflow_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void hsflow_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,373 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libhsflow.so (ctypes binding opticalflowhs_b200.HSFlow) and is checked against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * integer / exactly representable work (gray conversion, derivatives, synthetic frames, dot
+    masks): bit-exact;
+  * EXACT math iteration: bit-exact with the oracle (Kernels.cl op order, no contraction);
+  * FAST math iteration (the throughput path): max |du|,|dv| <= 1e-3 px and mean end-point-error
+    difference <= 1e-4 px after N iterations;
+  * temporally blocked kernel vs single-sweep kernel, batched vs single, strips vs whole: bit-identical.
+"""
+import numpy as np
+import pytest
+
+from conftest import iou
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAX = 1e-3      # px, north_star
+TOL_EPE = 1e-4      # px, north_star
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import opticalflowhs_b200 as pkg
+    return pkg
+
+
+@pytest.fixture()
+def eng(P):
+    e = P.HSFlow(0)
+    yield e
+    e.close()
+
+
+def epe_diff(u, v, uo, vo):
+    return abs(float(np.mean(np.hypot(u, v))) - float(np.mean(np.hypot(uo, vo))))
+
+
+def rand_frames(rng, h, w):
+    return rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h, w), dtype=np.uint8)
+
+
+ODD_SHAPES = [(1, 1), (1, 5), (7, 1), (5, 7), (17, 33), (9, 130), (66, 257), (40, 116), (23, 240), (31, 124)]
+
+# ---- derivatives: bit-exact -------------------------------------------------------------------
+
+def test_derivatives_gray_bit_exact(eng, oracle, frames):
+    for name in ("city", "bunny"):
+        g1, g2 = frames[f"{name}_1"], frames[f"{name}_2"]
+        eng.load_pair(g1, g2)
+        d = eng.read_derivatives()
+        o = oracle.derivatives(g1.astype(np.float32), g2.astype(np.float32))
+        for x, y in zip(d, o):
+            assert (bits(x) == bits(y)).all()
+
+
+def test_derivatives_bgr_fused_gray_bit_exact(eng, oracle, frames):
+    b1, b2 = frames["bunny_1_bgr"], frames["bunny_2_bgr"]
+    eng.load_pair(b1, b2)
+    d = eng.read_derivatives()
+    o = oracle.derivatives(oracle.bgr2gray(b1).astype(np.float32), oracle.bgr2gray(b2).astype(np.float32))
+    for x, y in zip(d, o):
+        assert (bits(x) == bits(y)).all()
+    rng = np.random.default_rng(3)
+    for (h, w) in [(3, 5), (9, 85), (4, 128), (6, 43)]:
+        b1 = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        b2 = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        eng.load_pair(b1, b2)
+        d = eng.read_derivatives()
+        o = oracle.derivatives(oracle.bgr2gray(b1).astype(np.float32), oracle.bgr2gray(b2).astype(np.float32))
+        for x, y in zip(d, o):
+            assert (bits(x) == bits(y)).all(), (h, w)
+
+
+def test_derivatives_odd_shapes_and_f32(eng, oracle):
+    rng = np.random.default_rng(5)
+    for (h, w) in ODD_SHAPES:
+        g1, g2 = rand_frames(rng, h, w)
+        eng.load_pair(g1, g2)
+        for x, y in zip(eng.read_derivatives(), oracle.derivatives(g1.astype(np.float32), g2.astype(np.float32))):
+            assert (bits(x) == bits(y)).all(), (h, w)
+        f1 = rng.standard_normal((h, w)).astype(np.float32) * 50
+        f2 = rng.standard_normal((h, w)).astype(np.float32) * 50
+        eng.load_pair(f1, f2)
+        for x, y in zip(eng.read_derivatives(), oracle.derivatives(f1, f2)):
+            assert (bits(x) == bits(y)).all(), (h, w)
+
+
+# ---- EXACT math: bit-exact with the oracle ------------------------------------------------------
+
+@pytest.mark.parametrize("update_v", [False, True])
+def test_exact_city_100_iterations_bitwise(eng, P, oracle, frames, update_v):
+    g1, g2 = frames["city_1"], frames["city_2"]
+    eng.set_math(P.MATH_EXACT).set_params(15.0, 100, P.STENCIL_CL8, update_v)
+    eng.load_pair(g1, g2).compute()
+    u, v = eng.read_uv()
+    uo, vo = oracle.run_cl(g1, g2, 15.0, 100, update_v)
+    assert (bits(u) == bits(uo)).all() and (bits(v) == bits(vo)).all()
+
+
+def test_exact_odd_shapes_and_warm_start_bitwise(eng, P, oracle):
+    rng = np.random.default_rng(11)
+    eng.set_math(P.MATH_EXACT)
+    for (h, w) in ODD_SHAPES:
+        g1, g2 = rand_frames(rng, h, w)
+        d = oracle.derivatives(g1.astype(np.float32), g2.astype(np.float32))
+        u0 = rng.standard_normal((h, w)).astype(np.float32)
+        v0 = rng.standard_normal((h, w)).astype(np.float32)
+        for upd in (True, False):
+            eng.set_params(3.0, 9, P.STENCIL_CL8, upd).set_warm_start(True)
+            eng.load_pair(g1, g2).write_uv(u0, v0)
+            eng.compute()
+            u, v = eng.read_uv()
+            uo, vo = oracle.jacobi(*d, 3.0, 9, upd, u0, v0)
+            assert (bits(u) == bits(uo)).all() and (bits(v) == bits(vo)).all(), (h, w, upd)
+    eng.set_warm_start(False)
+
+
+def test_exact_cv4_stencil_bitwise(eng, P, oracle, frames):
+    g1, g2 = frames["bunny_1"], frames["bunny_2"]
+    d = oracle.derivatives(g1.astype(np.float32), g2.astype(np.float32))
+    eng.set_math(P.MATH_EXACT).set_params(15.0, 20, P.STENCIL_CV4, True).set_lambda(0.1)
+    eng.load_pair(g1, g2).compute()
+    u, v = eng.read_uv()
+    uo, vo = oracle.jacobi_general(*d, np.float32(0.25), np.float32(0.0), np.float32(1.0) / np.float32(0.1), 20, True)
+    assert (bits(u) == bits(uo)).all() and (bits(v) == bits(vo)).all()
+
+
+# ---- golden masks through the GPU path ------------------------------------------------------------
+
+@pytest.mark.parametrize("name,n,dots", [("city", 10, 677), ("bunny", 10, 1373), ("bunny", 2, 924)])
+@pytest.mark.parametrize("math", ["exact", "fast"])
+def test_golden_masks_literal_mode(eng, P, frames, masks, name, n, dots, math):
+    eng.set_math(P.MATH_EXACT if math == "exact" else P.MATH_FAST).set_params(15.0, n, P.STENCIL_CL8, False)
+    eng.load_pair(frames[f"{name}_1"], frames[f"{name}_2"]).compute()
+    m, cnt = eng.dot_mask(0, 4, 0.5)
+    g = masks[f"{name}_cl_a15_n{n}"]
+    assert cnt == dots and iou(m, g) == 1.0
+    u, v = eng.read_uv()
+    assert not v.any()
+
+
+# ---- FAST math: north-star tolerance ------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["city", "bunny"])
+@pytest.mark.parametrize("T", [1, 2, 4, 8])
+def test_fast_within_tolerance_of_oracle(eng, P, oracle, frames, name, T):
+    g1, g2 = frames[f"{name}_1"], frames[f"{name}_2"]
+    uo, vo = oracle.run_cl(g1, g2, 15.0, 100, True)
+    eng.set_math(P.MATH_FAST).set_params(15.0, 100, P.STENCIL_CL8, True, T)
+    eng.load_pair(g1, g2).compute()
+    u, v = eng.read_uv()
+    assert np.abs(u - uo).max() <= TOL_MAX and np.abs(v - vo).max() <= TOL_MAX
+    assert epe_diff(u, v, uo, vo) <= TOL_EPE
+    # the formulation is in fact far tighter than the contract
+    assert np.abs(u - uo).max() <= 2e-5 and np.abs(v - vo).max() <= 2e-5
+
+
+def test_fast_fields_match_reference_generated_fixture(eng, P, fields, frames):
+    eng.set_math(P.MATH_FAST).set_params(15.0, 100, P.STENCIL_CL8, True, 4)
+    eng.load_pair(frames["city_1"], frames["city_2"]).compute()
+    u, v = eng.read_uv()
+    assert np.abs(u[::4, ::4] - fields["city_n100_full_u"]).max() <= TOL_MAX
+    assert np.abs(v[::4, ::4] - fields["city_n100_full_v"]).max() <= TOL_MAX
+
+
+# ---- temporally blocked kernel == single-sweep kernel, bit for bit ----------------------------------
+
+def run_fast(eng, P, g1, g2, n, T, kernel, stencil=0, chunk=0, wpc=0, alpha=15.0):
+    eng.set_math(P.MATH_FAST).set_kernel(kernel).set_tuning(chunk, wpc, 0)
+    eng.set_params(alpha, n, stencil, True, T)
+    eng.load_pair(g1, g2).compute()
+    out = eng.read_uv()
+    eng.set_kernel(0).set_tuning(0, 0, 0)
+    return out
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_stream_kernel_bit_identical_to_single_sweep(eng, P, T):
+    rng = np.random.default_rng(100 + T)
+    shapes = [(1, 1), (3, 9), (2, 130), (5, 116), (19, 113), (40, 124), (37, 250), (70, 131), (9, 500)]
+    for (h, w) in shapes:
+        g1, g2 = rand_frames(rng, h, w)
+        n = 2 * T + (1 if T > 1 else 0)          # full blocks plus a remainder block
+        ref = run_fast(eng, P, g1, g2, n, 1, 1)
+        for chunk, wpc in ((0, 0), (7, 3), (1, 1)):
+            out = run_fast(eng, P, g1, g2, n, T, 2, chunk=chunk, wpc=wpc)
+            assert (bits(out[0]) == bits(ref[0])).all() and (bits(out[1]) == bits(ref[1])).all(), (h, w, T, chunk, wpc)
+
+
+@pytest.mark.parametrize("T", [2, 4, 7])
+def test_stream_kernel_cv4_stencil_bit_identical(eng, P, T):
+    rng = np.random.default_rng(7 + T)
+    for (h, w) in [(11, 37), (33, 260)]:
+        g1, g2 = rand_frames(rng, h, w)
+        ref = run_fast(eng, P, g1, g2, 3 * T, 1, 1, stencil=1)
+        out = run_fast(eng, P, g1, g2, 3 * T, T, 2, stencil=1, chunk=5)
+        assert (bits(out[0]) == bits(ref[0])).all() and (bits(out[1]) == bits(ref[1])).all()
+
+
+def test_stream_kernel_real_frames_bit_identical(eng, P, frames):
+    g1, g2 = frames["city_1"], frames["city_2"]
+    ref = run_fast(eng, P, g1, g2, 100, 1, 1)
+    for T in (4, 6, 8):
+        out = run_fast(eng, P, g1, g2, 100, T, 0)
+        assert (bits(out[0]) == bits(ref[0])).all() and (bits(out[1]) == bits(ref[1])).all(), T
+
+
+# ---- batches ----------------------------------------------------------------------------------------
+
+def test_batch_with_sub_batches_equals_single_pairs(P, oracle):
+    W, H, n = 200, 96, 7
+    single = []
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, 21, P.STENCIL_CL8, True, 4)
+        for k in range(n):
+            f1, f2 = oracle.synth_pair(W, H, seed=1234 + k)
+            e.load_pair(f1, f2).compute()
+            single.append(e.read_uv())
+    for T, kern in ((4, 0), (1, 1)):
+        with P.HSFlow(0) as e:
+            e.set_tuning(0, 0, 3)                     # sub-batches of 3 -> 3 + 3 + 1
+            e.set_params(15.0, 21, P.STENCIL_CL8, True, T).set_kernel(kern)
+            e.configure(W, H, n)
+            for k in range(n):
+                e.set_frames(*oracle.synth_pair(W, H, seed=1234 + k), pair=k)
+            e.compute()
+            for k in range(n):
+                u, v = e.read_uv(k)
+                assert (bits(u) == bits(single[k][0])).all() and (bits(v) == bits(single[k][1])).all(), (T, k)
+
+
+def test_device_synthetic_frames_equal_oracle_generator(P, oracle):
+    W, H, n = 333, 77, 3
+    with P.HSFlow(0) as e:
+        e.configure(W, H, n).synth_frames(0, 0, 1234)
+        e.set_params(15.0, 0)
+        for k in range(n):
+            f1, f2 = oracle.synth_pair(W, H, seed=1234 + k)
+            o = oracle.derivatives(f1.astype(np.float32), f2.astype(np.float32))
+            for x, y in zip(e.read_derivatives(k), o):
+                assert (bits(x) == bits(y)).all()
+        # a strip of a taller frame
+        e.configure(W, 20, 1).synth_frames(200, 150, 99)
+        f1, f2 = oracle.synth_pair(W, 200, seed=99, row0=150, rows=20)
+        for x, y in zip(e.read_derivatives(0), oracle.derivatives(f1.astype(np.float32), f2.astype(np.float32))):
+            assert (bits(x) == bits(y)).all()
+
+
+def test_pipelined_host_batch_equals_per_pair_compute(P, oracle):
+    W, H, n = 256, 120, 11
+    frames = np.empty((n, 2, H, W), np.uint8)
+    for k in range(n):
+        frames[k, 0], frames[k, 1] = oracle.synth_pair(W, H, seed=50 + k)
+    u = np.empty((n, H, W), np.float32)
+    v = np.empty((n, H, W), np.float32)
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, 12, P.STENCIL_CL8, True, 4)
+        e.run_batch_host(frames, u, v)
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, 12, P.STENCIL_CL8, True, 4)
+        for k in range(n):
+            e.load_pair(frames[k, 0], frames[k, 1]).compute()
+            us, vs = e.read_uv()
+            assert (bits(u[k]) == bits(us)).all() and (bits(v[k]) == bits(vs)).all(), k
+
+
+# ---- strips: host-mediated halo exchange on one GPU ---------------------------------------------------
+
+@pytest.mark.parametrize("T,ghost", [(1, 1), (4, 4), (4, 8), (3, 6)])
+def test_row_strips_with_halo_exchange_equal_whole_frame(P, oracle, T, ghost):
+    W, H, N, nstrips = 180, 90, 2 * ghost + 3, 3
+    f1, f2 = oracle.synth_pair(W, H, seed=5)
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, T)
+        e.load_pair(f1, f2).compute()
+        whole = e.read_uv()
+    bounds = [H * k // nstrips for k in range(nstrips + 1)]
+    engs, ext = [], []
+    for k in range(nstrips):
+        lo, hi = bounds[k], bounds[k + 1]
+        a, b = max(lo - ghost, 0), min(hi + ghost + 1, H)     # +1 frame row for the j+1 derivative tap
+        e = P.HSFlow(0)
+        e.set_params(15.0, N, P.STENCIL_CL8, True, T)
+        e.configure(W, b - a, 1).set_strip(k == 0, k == nstrips - 1)
+        e.set_frames(f1[a:b], f2[a:b]).prepare()
+        engs.append(e)
+        ext.append((a, b, lo, hi))
+    done = 0
+    while done < N:
+        step = min(ghost, N - done)
+        for e in engs:
+            e.iterate(step)
+        done += step
+        cur = [e.read_uv() for e in engs]
+        gu, gv = np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
+        for (a, b, lo, hi), (u, v) in zip(ext, cur):
+            gu[lo:hi], gv[lo:hi] = u[lo - a:hi - a], v[lo - a:hi - a]
+        for e, (a, b, lo, hi) in zip(engs, ext):           # refresh every strip's ghost rows
+            e.write_uv(gu[a:b], gv[a:b]).halo_refreshed()
+    assert (bits(gu) == bits(whole[0])).all() and (bits(gv) == bits(whole[1])).all()
+    for e in engs:
+        e.close()
+
+
+# ---- OpenCV-mode path -------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name,floor", [("city", 0.99), ("bunny", 0.98)])
+def test_cv_mode_matches_restated_opencv_and_golden_masks(eng, P, oracle, frames, masks, name, floor):
+    g1, g2 = frames[f"{name}_1"], frames[f"{name}_2"]
+    uo, vo, it = oracle.run_cv(g1, g2, 0.1, 10, eps=0)
+    for math in (P.MATH_EXACT, P.MATH_FAST):
+        eng.set_math(math).set_deriv(P.DERIV_CV).set_params(15.0, 10, P.STENCIL_CV4, True, 4).set_lambda(0.1)
+        eng.load_pair(g1, g2).compute()
+        u, v = eng.read_uv()
+        assert np.abs(u - uo).max() <= TOL_MAX and np.abs(v - vo).max() <= TOL_MAX
+        m, _ = eng.dot_mask(0, 4, 1.0)
+        assert iou(m, masks[f"{name}_cv_l0.1_n10"]) >= floor
+    eng.set_deriv(P.DERIV_CL)
+
+
+# ---- full-size frames: window check through the domain of dependence -----------------------------------------
+
+@pytest.mark.parametrize("W,H,N,T", [(3840, 2160, 100, 4), (3840, 2160, 100, 8), (1920, 1080, 200, 6)])
+def test_full_size_frame_windows_against_oracle_crops(P, oracle, W, H, N, T):
+    K = 48
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, T)
+        e.configure(W, H, 1).synth_frames(0, 0, 1234).compute()
+        u, v = e.read_uv()
+    assert np.isfinite(u).all() and np.isfinite(v).all()
+    f1, f2 = oracle.synth_pair(W, H, seed=1234)
+    # windows at the corners, on strip seams (multiples of the valid strip width) and in the middle
+    vw = 128 - 2 * ((T + 3) // 4 * 4)
+    spots = [(0, 0), (H - K, W - K), (0, W - K), (H - K, 0), (H // 2, 7 * vw - K // 2), (H // 3, W // 2)]
+    for (y, x) in spots:
+        y0, y1 = max(y - N, 0), min(y + K + N, H)
+        x0, x1 = max(x - N, 0), min(x + K + N, W)
+        uo, vo = oracle.run_cl(f1[y0:y1, x0:x1], f2[y0:y1, x0:x1], 15.0, N, True)
+        # the derivative tap j+1/i+1 and N sweeps stay inside the crop except at true image edges
+        yy, xx = y - y0, x - x0
+        du = np.abs(u[y:y + K, x:x + K] - uo[yy:yy + K, xx:xx + K]).max()
+        dv = np.abs(v[y:y + K, x:x + K] - vo[yy:yy + K, xx:xx + K]).max()
+        assert du <= TOL_MAX and dv <= TOL_MAX, (y, x, du, dv)
+
+
+# ---- error behaviour of the boundary ------------------------------------------------------------------------------
+
+def test_error_codes_and_messages(eng, P):
+    with pytest.raises(P.HSFlowError):
+        eng.compute()                                   # nothing loaded
+    with pytest.raises(P.HSFlowError):
+        eng.set_params(15.0, -1)
+    with pytest.raises(P.HSFlowError):
+        eng.set_params(15.0, 10, 5)
+    with pytest.raises(P.HSFlowError):
+        eng.configure(0, 10, 1)
+    eng.configure(16, 16, 2)
+    with pytest.raises(P.HSFlowError):
+        eng.set_frames(np.zeros((16, 16), np.uint8), np.zeros((16, 16), np.uint8), pair=2)
+    with pytest.raises(P.HSFlowError):
+        P.HSFlow(999)
+    # zero iterations: u = v = 0 (cpp:331-332)
+    eng.set_params(15.0, 0)
+    eng.load_pair(np.full((8, 8), 3, np.uint8), np.full((8, 8), 9, np.uint8)).compute()
+    u, v = eng.read_uv()
+    assert not u.any() and not v.any()
+    assert eng.kernel_launches > 0
