@@ -257,30 +257,29 @@ class HSFlow:
         return self._L.hsflow_effective_temporal_block(self._h)
 
 
-def pinned_empty(shape, dtype):
-    """numpy array over cudaMallocHost memory (kept alive by the returned array's base)."""
-    dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    p = lib().hsflow_alloc_pinned(max(n, 1))
-    if not p:
-        raise HSFlowError(-4, "cudaMallocHost failed")
-    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+class _PinnedBuffer:
+    """cudaMallocHost block exposing the buffer protocol through ctypes; freed with the last numpy view."""
 
-    class _Owner:
-        def __init__(self, b, ptr):
-            self.b, self.ptr = b, ptr
+    def __init__(self, nbytes):
+        self.ptr = lib().hsflow_alloc_pinned(max(nbytes, 1))
+        if not self.ptr:
+            raise HSFlowError(-4, "cudaMallocHost failed")
+        self.nbytes = nbytes
 
-        def __del__(self):
-            try:
+    def __del__(self):
+        try:
+            if self.ptr:
                 lib().hsflow_free_pinned(self.ptr)
-            except Exception:
-                pass
-
-    owner = _Owner(buf, p)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    arr._hs_owner = owner if hasattr(arr, "__dict__") else None
-    _PINNED_OWNERS.append(owner)
-    return arr
+                self.ptr = None
+        except Exception:
+            pass
 
 
-_PINNED_OWNERS = []
+def pinned_empty(shape, dtype):
+    """numpy array over pinned (page-locked) host memory."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    owner = _PinnedBuffer(count * dtype.itemsize)
+    raw = (C.c_uint8 * max(owner.nbytes, 1)).from_address(owner.ptr)
+    raw._owner = owner                       # ctypes arrays accept attributes; numpy keeps `raw` as .base
+    return np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)
