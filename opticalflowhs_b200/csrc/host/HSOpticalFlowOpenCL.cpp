@@ -1,0 +1,227 @@
+// HSOpticalFlowOpenCL.cpp -- the drop-in host class on top of the C ABI (include/hsflow.h).
+//
+// Mirrors /root/reference/OpticalFlowHS/HSOpticalFlowOpenCL.cpp method by method; citations
+// "cpp:" refer to that file.  What changed underneath: no OpenCL runtime, frames go to the GPU
+// once as 8-bit pixels, grayscale conversion + derivatives are one fused kernel, the
+// `iterations` Jacobi sweeps run temporally blocked without any per-iteration host round trip
+// (the reference moves u and v over PCIe twice per iteration, cpp:483-501, 655-675).
+#include "../../../include/HSOpticalFlowOpenCL.hpp"
+
+#include <chrono>
+
+#include "hs_image.h"
+
+namespace {
+const unsigned char kCircleBGR[3] = {255, 0, 0};   // CV_RGB(0,0,255), cpp:3
+const unsigned char kLineBGR[3] = {0, 0, 255};     // CV_RGB(255,0,0), cpp:4
+
+inline void put(std::vector<unsigned char>& img, int w, int h, int x, int y, const unsigned char* c) {
+    if (x < 0 || y < 0 || x >= w || y >= h) return;
+    unsigned char* p = &img[((size_t)y * w + x) * 3];
+    p[0] = c[0]; p[1] = c[1]; p[2] = c[2];
+}
+void filledCircle2(std::vector<unsigned char>& img, int w, int h, int cx, int cy, const unsigned char* c) {
+    for (int dy = -2; dy <= 2; ++dy)              // cvCircle(.., 2, .., -1): the 21-pixel disc
+        for (int dx = -2; dx <= 2; ++dx)
+            if (dx * dx + dy * dy <= 5) put(img, w, h, cx + dx, cy + dy, c);
+}
+void line8(std::vector<unsigned char>& img, int w, int h, int x0, int y0, int x1, int y1, const unsigned char* c) {
+    int dx = std::abs(x1 - x0), sx = x0 < x1 ? 1 : -1, dy = -std::abs(y1 - y0), sy = y0 < y1 ? 1 : -1, err = dx + dy;
+    for (int guard = 0; guard < 1 << 20; ++guard) {   // Bresenham, 8-connected
+        put(img, w, h, x0, y0, c);
+        if (x0 == x1 && y0 == y1) break;
+        const int e2 = 2 * err;
+        if (e2 >= dy) { err += dy; x0 += sx; }
+        if (e2 <= dx) { err += dx; y0 += sy; }
+    }
+}
+}  // namespace
+
+// Shared with OpticalFlowOpenCV.cpp: the drawing loop of cpp:758-770 / cv.cpp:32-46.
+void hsflow_host_draw(std::vector<unsigned char>& img, int w, int h, const float* u, const float* v,
+                      float thr, float lineScale) {
+    img.assign((size_t)w * h * 3, 0);             // cvZero(imgFlow)
+    const int step = 4;
+    for (int i = 0; i < h; i += step)
+        for (int j = 0; j < w; j += step) {
+            const float a = u[(size_t)i * w + j], b = v[(size_t)i * w + j];
+            if (a > thr || b > thr || a < -thr || b < -thr) {
+                filledCircle2(img, w, h, j, i, kCircleBGR);
+                line8(img, w, h, j, i, (int)(j + a * lineScale), (int)(i + b * lineScale), kLineBGR);
+            }
+        }
+}
+
+HSOpticalFlowOpenCL::HSOpticalFlowOpenCL(const char* nm, char* src_, char* in1, char* in2, char* out,
+                                         float alp, int it, int gs, char* dType)
+    : name(nm ? nm : ""), pixelData(NULL), inputImageData1(NULL), inputImageData2(NULL), u(NULL), v(NULL),
+      alpha(alp), engine(NULL), width(0), height(0), blockSizeX((size_t)gs), blockSizeY(1),
+      src(src_), input1(in1), input2(in2), output(out), iterations(it),
+      useGpu(!(dType && strcmp(dType, "CPU") == 0)), totalTime(0.0) {}
+
+HSOpticalFlowOpenCL::HSOpticalFlowOpenCL(const char* nm, char* src_, float alp, int it, int gs, char* dType)
+    : name(nm ? nm : ""), pixelData(NULL), inputImageData1(NULL), inputImageData2(NULL), u(NULL), v(NULL),
+      alpha(alp), engine(NULL), width(0), height(0), blockSizeX((size_t)gs), blockSizeY(1),
+      src(src_), input1(NULL), input2(NULL), output(NULL), iterations(it),
+      useGpu(!(dType && strcmp(dType, "CPU") == 0)), totalTime(0.0) {}
+
+HSOpticalFlowOpenCL::~HSOpticalFlowOpenCL() {}
+
+int HSOpticalFlowOpenCL::initialize() { return SDK_SUCCESS; }   // cpp:681-704: only registered a dead "-i" option
+int HSOpticalFlowOpenCL::setup() { return SDK_SUCCESS; }        // cpp:895
+int HSOpticalFlowOpenCL::verifyResults() { return SDK_SUCCESS; }   // cpp:894 (stub in the reference too)
+void HSOpticalFlowOpenCL::printStats() {
+    std::cout << name << ": " << width << "x" << height << ", alpha " << alpha << ", " << iterations
+              << " iterations, " << totalTime << " ms" << std::endl;
+}
+
+// cvLoadImage + cvCvtColor(BGR2GRAY) (cpp:721-728): the image is decoded to BGR (or gray) bytes.
+int HSOpticalFlowOpenCL::loadGray(const char* path, std::vector<unsigned char>& out, int& w, int& h) {
+    int ch = 0;
+    uint8_t* data = NULL;
+    if (hsimg_read(path, &w, &h, &ch, &data) != 0) return -1;
+    out.resize((size_t)w * h);
+    if (ch == 1) memcpy(out.data(), data, out.size());
+    else for (size_t k = 0; k < out.size(); ++k)      // OpenCV 2.1 fixed-point BGR2GRAY
+        out[k] = (unsigned char)((data[3 * k] * 1868 + data[3 * k + 1] * 9617 + data[3 * k + 2] * 4899 + 8192) >> 14);
+    hsimg_free(data);
+    return 0;
+}
+
+// cpp:6-45: stage the current gray frame as float4 (lane 0 = value) into a fresh plane.
+int HSOpticalFlowOpenCL::readInputImage(cl_float4** inputImageData) {
+    if (!inputImageData || gray.empty()) return SDK_FAILURE;
+    const size_t n = (size_t)width * height;
+    free(pixelData);
+    pixelData = (cl_float4*)calloc(n, sizeof(cl_float4));
+    *inputImageData = (cl_float4*)malloc(n * sizeof(cl_float4));
+    if (!pixelData || !*inputImageData) return SDK_FAILURE;
+    for (size_t k = 0; k < n; ++k) pixelData[k].s[0] = (cl_float)gray[k];
+    memcpy(*inputImageData, pixelData, n * sizeof(cl_float4));
+    return SDK_SUCCESS;
+}
+// cpp:47-64: same into an existing plane.
+int HSOpticalFlowOpenCL::readInputFrame(cl_float4** inputImageData) {
+    if (!inputImageData || !*inputImageData || !pixelData || gray.empty()) return SDK_FAILURE;
+    const size_t n = (size_t)width * height;
+    memset(pixelData, 0, n * sizeof(cl_float4));
+    for (size_t k = 0; k < n; ++k) pixelData[k].s[0] = (cl_float)gray[k];
+    memcpy(*inputImageData, pixelData, n * sizeof(cl_float4));
+    return 0;
+}
+
+// cpp:67-319: context, queue, 9 buffers, program build -> one engine handle.
+int HSOpticalFlowOpenCL::setupCL() {
+    if (engine) return SDK_SUCCESS;
+    if (hsflow_create(0, &engine) != HSFLOW_OK) {
+        std::cout << "hsflow: " << hsflow_last_error() << std::endl;
+        engine = NULL;
+        return SDK_FAILURE;
+    }
+    // Defaults reproduce the shipped kernel literally: u_v_updateKernel never writes v
+    // (Kernels.cl:87-89).  HSFLOW_UPDATE_V=1 selects the full Horn-Schunck update.
+    const char* uv = getenv("HSFLOW_UPDATE_V");
+    const char* ex = getenv("HSFLOW_EXACT");
+    hsflow_set_math(engine, (ex && atoi(ex)) ? HSFLOW_MATH_EXACT : HSFLOW_MATH_FAST);
+    if (hsflow_set_params(engine, alpha, iterations, HSFLOW_STENCIL_CL8, (uv && atoi(uv)) ? 1 : 0, 0) != HSFLOW_OK) {
+        std::cout << "hsflow: " << hsflow_last_error() << std::endl;
+        return SDK_FAILURE;
+    }
+    return SDK_SUCCESS;
+}
+
+// cpp:321-474: zero u/v, upload both frames, derivative kernel.
+int HSOpticalFlowOpenCL::runDerivatives() {
+    if (!engine || !inputImageData1 || !inputImageData2) return SDK_FAILURE;
+    const size_t n = (size_t)width * height;
+    std::vector<float> a(n), b(n);
+    for (size_t k = 0; k < n; ++k) { a[k] = inputImageData1[k].s[0]; b[k] = inputImageData2[k].s[0]; }
+    if (hsflow_load_pair_f32(engine, a.data(), b.data(), (int)width, (int)height, 0) != HSFLOW_OK) return SDK_FAILURE;
+    return hsflow_prepare(engine) == HSFLOW_OK ? SDK_SUCCESS : SDK_FAILURE;
+}
+// cpp:476-679: one iteration (no PCIe traffic here; results stay on the device).
+int HSOpticalFlowOpenCL::runCLKernels() {
+    if (!engine) return SDK_FAILURE;
+    return hsflow_iterate(engine, 1) == HSFLOW_OK ? SDK_SUCCESS : SDK_FAILURE;
+}
+
+int HSOpticalFlowOpenCL::drawAndSave(const char* path) {
+    std::vector<unsigned char> img;
+    hsflow_host_draw(img, (int)width, (int)height, uHost.data(), vHost.data(), 0.5f, 1.0f);   // cpp:762-770
+    if (hsimg_write(path, img.data(), (int)width, (int)height, 3) != 0) {
+        std::cout << "Output image error: " << hsimg_last_error() << std::endl;
+        return -1;
+    }
+    return 0;
+}
+
+// cpp:706-847
+int HSOpticalFlowOpenCL::run() {
+    if (!src) return SDK_FAILURE;
+    if (strcmp(src, "-hd") != 0) return runFrameSequence();
+    int w1 = 0, h1 = 0, w2 = 0, h2 = 0;
+    std::vector<unsigned char> g1, g2;
+    if (!input1 || loadGray(input1, g1, w1, h1) != 0) { std::cout << "Input image error.\n"; return -1; }   // cpp:722-725
+    if (!input2 || loadGray(input2, g2, w2, h2) != 0 || w2 != w1 || h2 != h1) { std::cout << "Input image error.\n"; return -1; }
+    width = (cl_uint)w1; height = (cl_uint)h1;
+    gray = g2;
+    std::cout << "przed setupCL\n";
+    if (setupCL() != SDK_SUCCESS) return SDK_FAILURE;
+    std::cout << "po setupCL\n";
+    const size_t n = (size_t)width * height;
+    uHost.assign(n, 0.f); vHost.assign(n, 0.f);
+    // timed region of cpp:748-752: upload, derivatives, all iterations, read-back
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = hsflow_load_pair_gray8(engine, g1.data(), g2.data(), w1, h1, 0);
+    if (rc == HSFLOW_OK) rc = hsflow_compute(engine);
+    if (rc == HSFLOW_OK) rc = hsflow_read_uv(engine, 0, uHost.data(), vHost.data(), 0);
+    totalTime = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (rc != HSFLOW_OK) { std::cout << "hsflow: " << hsflow_last_error() << std::endl; return SDK_FAILURE; }
+    std::cout << "Avg time: " << totalTime << " [ms]" << std::endl;   // cpp:755
+    if (output && drawAndSave(output) != 0) return -1;
+    return 0;
+}
+
+// Camera branch (cpp:775-845).  There is no capture device here: consecutive frames are read
+// from files named by HSFLOW_FRAMES (printf pattern, e.g. "frames/%04d.pgm", starting at 0),
+// each new frame paired with the previous one (cpp:834), until a file is missing.
+int HSOpticalFlowOpenCL::runFrameSequence() {
+    const char* pattern = getenv("HSFLOW_FRAMES");
+    if (!pattern) { fprintf(stderr, "ERROR: capture is NULL \n"); return -1; }   // cpp:779-783
+    char path[1024];
+    std::vector<unsigned char> prev, cur;
+    int w = 0, h = 0, count = 0;
+    snprintf(path, sizeof path, pattern, 0);
+    if (loadGray(path, prev, w, h) != 0) { fprintf(stderr, "ERROR: frame is null...\n"); return -1; }
+    width = (cl_uint)w; height = (cl_uint)h;
+    if (setupCL() != SDK_SUCCESS) return SDK_FAILURE;
+    uHost.assign((size_t)w * h, 0.f); vHost.assign((size_t)w * h, 0.f);
+    double ms = 0;
+    for (int k = 1;; ++k) {
+        int w2 = 0, h2 = 0;
+        snprintf(path, sizeof path, pattern, k);
+        if (loadGray(path, cur, w2, h2) != 0 || w2 != w || h2 != h) break;
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = hsflow_load_pair_gray8(engine, prev.data(), cur.data(), w, h, 0);   // u, v re-zeroed per pair (cpp:331-332)
+        if (rc == HSFLOW_OK) rc = hsflow_compute(engine);
+        if (rc == HSFLOW_OK) rc = hsflow_read_uv(engine, 0, uHost.data(), vHost.data(), 0);
+        ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (rc != HSFLOW_OK) { std::cout << "hsflow: " << hsflow_last_error() << std::endl; return SDK_FAILURE; }
+        const char* outp = getenv("HSFLOW_FRAMES_OUT");
+        if (outp) { char op[1024]; snprintf(op, sizeof op, outp, k); drawAndSave(op); }
+        prev.swap(cur);                                                              // cpp:834
+        ++count;
+    }
+    gray = prev;
+    totalTime = count ? ms / count : 0.0;
+    std::cout << "Avg time: " << totalTime << " [ms]" << std::endl;                  // cpp:838
+    return SDK_SUCCESS;
+}
+
+// cpp:849-892
+int HSOpticalFlowOpenCL::cleanup() {
+    if (engine) { hsflow_destroy(engine); engine = NULL; }
+    free(pixelData); free(inputImageData1); free(inputImageData2); free(u); free(v);
+    pixelData = inputImageData1 = inputImageData2 = u = v = NULL;
+    return SDK_SUCCESS;
+}
