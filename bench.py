@@ -278,13 +278,130 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: one 16384 x 16384 frame pair, 500 iterations, row strips + halo exchange
+# ------------------------------------------------------------------------------------------------
+
+def run_strip16k(args, rank, world, local_rank):
+    import torch
+    import opticalflowhs_b200 as P
+    from opticalflowhs_b200.sharding import StripSolver, ideal_strip_time_s
+    W = H = 16384
+    N = args.iterations or 500
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng = P.HSFlow(local_rank)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_params(ALPHA, N, P.STENCIL_CL8, True, args.temporal_block)
+    T = eng.temporal_block
+    ghost = args.ghost or T
+    solver = StripSolver(eng, W, H, rank, world, ghost, dist=dist)
+    solver.load_synth(1234)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        solver.run(min(N, 4 * ghost))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        solver.run(N)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    launches = eng.kernel_launches - l0
+    value = float(W) * H * N / (ms * 1e-3) / 1e6
+    peak, peak_src = measured_peaks()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic {W}x{H} single frame pair, alpha={ALPHA:g}, {N} iterations, FULL mode, "
+                                   f"row strips over {world} GPU(s) with halo exchange every {ghost} iterations "
+                                   "(BASELINE.json configs[4])", "temporal_block": T, "ghost_rows": ghost,
+                       "halo_bytes_sent_per_exchange": solver.plan.halo_bytes_per_exchange(W), "exchanges": solver.exchanges},
+            "roofline": {"bound": "hbm", "achieved": value * 1e6 * ALG_BYTES_PER_PX_IT / 1e9 / world, "peak": peak,
+                         "unit": "GB/s", "frac": value * 1e6 * ALG_BYTES_PER_PX_IT / 1e9 / world / peak, "traffic": None,
+                         "peak_source": peak_src, "note": "per-GPU unfused-equivalent bandwidth of the whole strip job"},
+            "ideal_ms_at_hbm_peak": 1e3 * ideal_strip_time_s(W, H, N, world, peak),
+            "gpu_launches": int(launches), "clocks": clocks}), flush=True)
+    eng.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: 1920x1080 pair, 200 iterations, temporal-blocking sweep on one GPU
+# ------------------------------------------------------------------------------------------------
+
+def run_sweep1080p(args, rank, world, local_rank):
+    import torch
+    import opticalflowhs_b200 as P
+    if rank != 0:
+        return
+    W, H, N = 1920, 1080, args.iterations or 200
+    torch.cuda.set_device(local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+    rows = []
+    with P.HSFlow(local_rank) as eng:
+        eng.configure(W, H, 1).synth_frames(0, 0, 1234)
+        for kern, T in [(1, 1)] + [(2, t) for t in range(1, 9)]:
+            eng.set_kernel(kern).set_params(ALPHA, N, P.STENCIL_CL8, True, T)
+            times = []
+            for rep in range(args.warmup + args.steps):
+                flush.fill_(rep & 255)                                    # 1080p planes (58 MB) fit L2: flush between reps
+                torch.cuda.synchronize()
+                eng.prepare(); eng.iterate(N); eng.sync()
+                if rep >= args.warmup:
+                    times.append(eng.last_ms(2))
+            ms = statistics.median(times)
+            rows.append({"kernel": "k_jacobi1" if kern == 1 else "k_jacobi_stream", "T": T, "ms": ms,
+                         "mpx_it_per_s": W * H * N / ms / 1e3, "effective_gbs": W * H * N * ALG_BYTES_PER_PX_IT / ms / 1e6})
+    best = max(rows, key=lambda r: r["mpx_it_per_s"])
+    peak, peak_src = measured_peaks()
+    print(json.dumps({"metric": METRIC, "value": best["mpx_it_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": best["ms"], "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"synthetic {W}x{H} frame pair, {N} iterations, temporal-block sweep "
+                                             "(BASELINE.json configs[2]); L2 flushed between repetitions, iterations "
+                                             "within a repetition run L2-warm (58 MB working set < 126 MB L2)"},
+                      "roofline": {"bound": "hbm", "achieved": best["effective_gbs"], "peak": peak, "unit": "GB/s",
+                                   "frac": best["effective_gbs"] / peak, "traffic": None, "peak_source": peak_src},
+                      "sweep": rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pairs4k", choices=["pairs4k", "strip16k", "sweep1080p"],
+                    help="pairs4k: BASELINE configs[3] (default, the headline); strip16k: configs[4], one 16384^2 frame "
+                         "row-strip sharded with NVLink halo exchange; sweep1080p: configs[2], temporal-block sweep")
     ap.add_argument("--pairs", type=int, default=256, help="4K frame pairs per GPU and step")
+    ap.add_argument("--ghost", type=int, default=0, help="strip16k: ghost rows per seam = iterations per halo exchange (0: = T)")
+    ap.add_argument("--iterations", type=int, default=0, help="strip16k / sweep1080p: override the iteration count")
     ap.add_argument("--e2e-pairs", type=int, default=64)
     ap.add_argument("--temporal-block", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -302,6 +419,10 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.workload == "strip16k":
+        run_strip16k(args, rank, world, local_rank)
+    elif args.workload == "sweep1080p":
+        run_sweep1080p(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -1,0 +1,153 @@
+"""Sharding layer of the Horn-Schunck engine (the reference has no multi-device code).
+
+One process per GPU (torchrun), `torch.distributed` only for plumbing:
+
+  * pair sharding  -- independent frame pairs, contiguous blocks of ceil(P/n) pairs per rank, no
+                      data-path collective (`pair_block`);
+  * row strips     -- one very large frame cut into `world` horizontal strips.  Every rank keeps
+                      `ghost` extra rows of u, v (and of the frames / coefficients) on each inner
+                      seam, advances `ghost` Jacobi iterations per exchange with the temporally
+                      blocked kernel and then swaps seam rows with its two neighbours
+                      (`StripSolver.exchange`: NCCL send/recv over NVLink, non-periodic).  The
+                      result is bit-identical to the single-GPU run because every pixel sees the
+                      same operation sequence.
+
+The solver talks to an engine object with the HSFlow method set (configure, set_strip,
+set_frames / synth_frames, prepare, iterate, halo_refreshed, uv_tensors); the CPU test-suite
+plugs a numpy stand-in into the same exchange code under the gloo backend.
+"""
+import math
+
+
+def pair_block(n_pairs, world, rank):
+    """Contiguous block [lo, hi) of frame pairs owned by `rank` (ceil(P/n) per rank)."""
+    per = (n_pairs + world - 1) // world
+    lo = min(rank * per, n_pairs)
+    return lo, min(lo + per, n_pairs)
+
+
+class StripPlan:
+    """Rows of a W x H frame owned by one rank, and the buffer rows (owned + ghosts) it holds.
+
+    own  = [lo, hi)          rows this rank is responsible for
+    buf  = [a, b)            rows resident on the rank: `ghost` rows above lo, `ghost + 1` rows
+                             below hi (the extra row feeds the j+1 tap of the derivative
+                             stencil, Kernels.cl:26), clipped at the true image edges
+    """
+
+    def __init__(self, height, world, rank, ghost):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError("bad rank/world")
+        base = height // world
+        if base < ghost + 1:
+            raise ValueError(f"strips of {base} rows are thinner than ghost+1 = {ghost + 1}")
+        self.height, self.world, self.rank, self.ghost = height, world, rank, ghost
+        self.lo = rank * base
+        self.hi = height if rank == world - 1 else (rank + 1) * base
+        self.a = max(self.lo - ghost, 0)
+        self.b = min(self.hi + ghost + 1, height)
+        self.is_top = rank == 0
+        self.is_bottom = rank == world - 1
+
+    @property
+    def rows(self):
+        return self.b - self.a
+
+    @property
+    def top_ghost(self):
+        return self.lo - self.a
+
+    @property
+    def bottom_ghost(self):
+        return self.b - self.hi
+
+    def halo_bytes_per_exchange(self, width):
+        """fp32 bytes this rank SENDS per exchange (u and v)."""
+        rows = (0 if self.is_top else self.ghost + 1) + (0 if self.is_bottom else self.ghost)
+        return rows * width * 4 * 2
+
+
+class DeviceView:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def engine_uv_tensors(engine, device_index):
+    """Current u/v planes of an HSFlow handle as torch tensors [rows, pitch] (no copy)."""
+    import torch
+    u, v, rp, _ = engine.device_uv()
+    dev = torch.device("cuda", device_index)
+    tu = torch.as_tensor(DeviceView(u, (engine.H, rp)), device=dev)
+    tv = torch.as_tensor(DeviceView(v, (engine.H, rp)), device=dev)
+    return tu, tv
+
+
+class StripSolver:
+    """Row-strip Horn-Schunck over `world` ranks with per-temporal-block halo exchange."""
+
+    def __init__(self, engine, width, height, rank, world, ghost, dist=None, uv_tensors=None):
+        self.e, self.W, self.H = engine, width, height
+        self.plan = StripPlan(height, world, rank, ghost)
+        self.dist = dist
+        self._uv = uv_tensors or (lambda: engine_uv_tensors(engine, engine.device))
+        self.exchanges = 0
+        engine.configure(width, self.plan.rows, 1)
+        engine.set_strip(self.plan.is_top, self.plan.is_bottom)
+
+    # ---- frames -------------------------------------------------------------------------------
+    def load_synth(self, seed):
+        self.e.synth_frames(self.H, self.plan.a, seed)
+
+    def load_frames(self, f1, f2):
+        """f1, f2: the FULL frames (numpy); only this rank's rows are uploaded."""
+        self.e.set_frames(f1[self.plan.a:self.plan.b], f2[self.plan.a:self.plan.b])
+
+    # ---- halo exchange ---------------------------------------------------------------------------
+    def exchange(self):
+        """Swap seam rows of the current u/v planes with the upper and lower neighbour."""
+        p, g = self.plan, self.plan.ghost
+        if p.world > 1:
+            dist = self.dist
+            tu, tv = self._uv()
+            ops = []
+            for t in (tu, tv):
+                if not p.is_top:      # upper neighbour's bottom ghost holds g+1 rows; my top ghost holds g rows
+                    ops.append(dist.P2POp(dist.isend, t[p.top_ghost:p.top_ghost + g + 1], p.rank - 1))
+                    ops.append(dist.P2POp(dist.irecv, t[0:p.top_ghost], p.rank - 1))
+                if not p.is_bottom:
+                    own_end = p.hi - p.a
+                    ops.append(dist.P2POp(dist.isend, t[own_end - g:own_end], p.rank + 1))
+                    ops.append(dist.P2POp(dist.irecv, t[own_end:own_end + p.bottom_ghost], p.rank + 1))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            self.exchanges += 1
+        self.e.halo_refreshed()
+
+    # ---- driver ---------------------------------------------------------------------------------
+    def run(self, iterations):
+        self.e.prepare()
+        done = 0
+        while done < iterations:
+            step = min(self.plan.ghost, iterations - done)
+            self.e.iterate(step)
+            done += step
+            if done < iterations:
+                self.exchange()
+        return self
+
+    def owned_rows(self, plane):
+        """Slice of a [rows, ...] buffer plane that this rank owns."""
+        return plane[self.plan.lo - self.plan.a:self.plan.hi - self.plan.a]
+
+
+def ideal_strip_time_s(width, height, iterations, world, hbm_gbs, bytes_per_px_it=28.0):
+    """Lower bound of SURVEY.md 8d: algorithmic bytes / (world x HBM bandwidth)."""
+    return width * height * iterations * bytes_per_px_it / (hbm_gbs * 1e9) / world
+
+
+def halo_fraction(width, rows_per_rank, ghost):
+    """Share of redundant (ghost) rows a rank computes per block, averaged over the block."""
+    return (ghost + 1) / float(rows_per_rank) if rows_per_rank else math.inf
