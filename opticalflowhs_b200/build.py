@@ -17,7 +17,7 @@ HEADERS = ["hs_common.cuh", "hs_launch.h", os.path.join("..", "..", "include", "
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-    "--fmad=false",           # arithmetic is written with explicit *_rn intrinsics; never contract anything else
+    "-diag-suppress", "3288", "--fmad=false",           # arithmetic is written with explicit *_rn intrinsics; never contract anything else
 ]
 
 

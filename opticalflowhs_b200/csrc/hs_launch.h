@@ -68,7 +68,8 @@ constexpr int kMaxT = 8;
 constexpr int kStreamRowsPerBox = 2;   // TMA box = 128 columns x 2 rows
 StreamGeom stream_geometry(int T);
 cudaError_t stream_prepare(int device);     // opt in to large dynamic shared memory for every instantiation
-// maps: u source, v source, coefficient planes a,b,c.  warps_per_cta in 1..8.
+int stream_warps_per_sm(int T, int stencil, int warps_per_cta);   // resident warps per SM (occupancy API)
+// maps: u source, v source, coefficient planes a,b,c.  warps_per_cta in 1..4.
 cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tm_u, const CUtensorMap& tm_v,
                                  const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_c,
                                  StreamArgs A, int pairs, int warps_per_cta, cudaStream_t s);

@@ -23,6 +23,7 @@
 // traffic 28 B / T per pixel-iteration (+ halo overhead).  tests/stream_model.py is the numpy
 // model of exactly this bookkeeping.
 #include <type_traits>
+#include <utility>
 
 #include "hs_common.cuh"
 #include "hs_launch.h"
@@ -70,25 +71,39 @@ template <int T, int RG, int NGC, int NGUV> struct StreamCfg {
     static constexpr int NRUV = NGUV * RG;                  // u/v ring rows
     static constexpr int ROWB = kStripW * 4;                // bytes per ring row
     static constexpr int SMEM_WARP = (3 * NRC + 2 * NRUV) * ROWB + 128;   // + mbarriers
-    static_assert(NGC * RG > T + RG, "coefficient ring too short for the stage lag");
+    // a coefficient group is refilled at the end of the RG-tick body that retires it; it must
+    // have been issued at least one body before it is needed
+    static_assert((NGC - 1) * RG >= T + 2, "coefficient ring too short for the stage lag");
     static_assert(NGC + NGUV <= 16, "barrier block is 128 bytes");
+    static_assert(RG == 2, "the steady-state body is written for 2-row TMA boxes");
 };
 template <int T> struct DefaultCfg {
     static constexpr int RG = kStreamRowsPerBox;
-    static constexpr int NGC = (T + RG - 1) / RG + 2;
-    static constexpr int NGUV = 3;
+    static constexpr int NGC = T <= 4 ? 4 : 6;              // 8 or 12 coefficient rows
+    static constexpr int NGUV = 2;                          // 4 u/v rows
     using type = StreamCfg<T, RG, NGC, NGUV>;
 };
 
+// ring offset arithmetic in bytes: power-of-two rings wrap with one AND
+template <int SIZE_BYTES> __device__ __forceinline__ int wrap_down(int off) {   // off in (-SIZE, SIZE)
+    if ((SIZE_BYTES & (SIZE_BYTES - 1)) == 0) return off & (SIZE_BYTES - 1);
+    return off < 0 ? off + SIZE_BYTES : off;
+}
+template <int SIZE_BYTES> __device__ __forceinline__ int wrap_up(int off) {     // off in [0, 2*SIZE)
+    if ((SIZE_BYTES & (SIZE_BYTES - 1)) == 0) return off & (SIZE_BYTES - 1);
+    return off >= SIZE_BYTES ? off - SIZE_BYTES : off;
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------
 template <int T, int ST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
                 const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_c, const StreamArgs A) {
     using C = typename DefaultCfg<T>::type;
     constexpr int RG = DefaultCfg<T>::RG, NGC = DefaultCfg<T>::NGC, NGUV = DefaultCfg<T>::NGUV;
-    constexpr int NRC = C::NRC, NRUV = C::NRUV;
+    constexpr int NRC = C::NRC, NRUV = C::NRUV, ROWB = C::ROWB;
+    constexpr int CB = NRC * ROWB, UB = NRUV * ROWB;        // ring sizes in bytes
     extern __shared__ __align__(128) uint8_t smem_raw[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -111,30 +126,29 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
     const bool edge = (sx == 0) || (x0 + kStripW - 1 >= W - 1);
     const bool wmis = (W & 3) != 0;
 
-    float* sa = reinterpret_cast<float*>(smem_raw + (size_t)warp * C::SMEM_WARP);
-    float* sb = sa + NRC * kStripW;
-    float* sc = sb + NRC * kStripW;
-    float* su = sc + NRC * kStripW;
-    float* sv = su + NRUV * kStripW;
-    const uint32_t bar0 = smem_u32(sv + NRUV * kStripW);   // cbar[NGC] then uvbar[NGUV]
-    const uint32_t sa32 = smem_u32(sa), sb32 = smem_u32(sb), sc32 = smem_u32(sc), su32 = smem_u32(su), sv32 = smem_u32(sv);
+    uint8_t* wsm = smem_raw + (size_t)warp * C::SMEM_WARP;
+    // byte layout per warp: a ring | b ring | c ring | u ring | v ring | mbarriers
+    const uint8_t* sa_l = wsm + lane * 16;                  // this lane's 16-byte column group
+    const uint8_t* su_l = wsm + 3 * CB + lane * 16;
+    const uint32_t sa32 = smem_u32(wsm), su32 = sa32 + 3 * CB;
+    const uint32_t bar0 = su32 + 2 * UB;                    // cbar[NGC] then uvbar[NGUV]
 
     auto issue_coef = [&](int g) {                 // lane 0 only
         const int slot = (g - g0) % NGC;
         const uint32_t bar = bar0 + 8u * slot;
-        mbar_expect_tx(bar, 3u * RG * C::ROWB);
-        const uint32_t off = (uint32_t)slot * RG * C::ROWB;
+        mbar_expect_tx(bar, 3u * RG * ROWB);
+        const uint32_t off = (uint32_t)slot * RG * ROWB;
         tma_load_3d(sa32 + off, &tm_a, x0, g * RG, A.z_c0 + z, bar);
-        tma_load_3d(sb32 + off, &tm_b, x0, g * RG, A.z_c0 + z, bar);
-        tma_load_3d(sc32 + off, &tm_c, x0, g * RG, A.z_c0 + z, bar);
+        tma_load_3d(sa32 + CB + off, &tm_b, x0, g * RG, A.z_c0 + z, bar);
+        tma_load_3d(sa32 + 2 * CB + off, &tm_c, x0, g * RG, A.z_c0 + z, bar);
     };
     auto issue_uv = [&](int g) {                   // lane 0 only
         const int slot = (g - g0) % NGUV;
         const uint32_t bar = bar0 + 8u * (NGC + slot);
-        mbar_expect_tx(bar, 2u * RG * C::ROWB);
-        const uint32_t off = (uint32_t)slot * RG * C::ROWB;
+        mbar_expect_tx(bar, 2u * RG * ROWB);
+        const uint32_t off = (uint32_t)slot * RG * ROWB;
         tma_load_3d(su32 + off, &tm_u, x0, g * RG, A.z_in0 + z, bar);
-        tma_load_3d(sv32 + off, &tm_v, x0, g * RG, A.z_in0 + z, bar);
+        tma_load_3d(su32 + UB + off, &tm_v, x0, g * RG, A.z_in0 + z, bar);
     };
 
     if (lane == 0) {
@@ -161,20 +175,49 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
     float* uo = A.u_out + (size_t)z * A.out_pair_pitch + col0;
     float* vo = A.v_out + (size_t)z * A.out_pair_pitch + col0;
 
-    auto tick = [&](auto gen_tag, const int r) {
-        constexpr bool GEN = decltype(gen_tag)::value;
+    // one stage-row in steady state: time step S of one row (cu, cv) -> time step S+1 of the row
+    // above it, written back into cu, cv.  coff = byte offset of that row's coefficients.
+    auto stage_row = [&](auto edge_tag, auto s_tag, float (&cu)[4], float (&cv)[4], const int coff) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        constexpr int S = decltype(s_tag)::value;
+        if (EDGE && wmis) { sanitize_right(cu, col0, W); sanitize_right(cv, col0, W); }
+        float lu = __shfl_up_sync(kFull, cu[3], 1), ru = __shfl_down_sync(kFull, cu[0], 1);
+        float lv = __shfl_up_sync(kFull, cv[3], 1), rv = __shfl_down_sync(kFull, cv[0], 1);
+        if (EDGE) { clamp_lr(cu, col0, W, lu, ru); clamp_lr(cv, col0, W, lv, rv); }
+        const float4 ka = *reinterpret_cast<const float4*>(sa_l + coff);
+        const float4 kb = *reinterpret_cast<const float4*>(sa_l + CB + coff);
+        const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * CB + coff);
+        const float hu[4] = {__fadd_rn(lu, cu[1]), __fadd_rn(cu[0], cu[2]), __fadd_rn(cu[1], cu[3]), __fadd_rn(cu[2], ru)};
+        const float hv[4] = {__fadd_rn(lv, cv[1]), __fadd_rn(cv[0], cv[2]), __fadd_rn(cv[1], cv[3]), __fadd_rn(cv[2], rv)};
+        float ub[4], vb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float Gu = rowG<ST>(cu[j], hu[j]), Gv = rowG<ST>(cv[j], hv[j]);
+            ub[j] = combine<ST>(p[S][j], Gu);
+            vb[j] = combine<ST>(p[S][4 + j], Gv);
+            p[S][j] = pOf<ST>(g[S][j], hu[j]); g[S][j] = Gu;
+            p[S][4 + j] = pOf<ST>(g[S][4 + j], hv[j]); g[S][4 + j] = Gv;
+        }
+        update_fast(ub[0], vb[0], ka.x, kb.x, kc.x, cu[0], cv[0]);
+        update_fast(ub[1], vb[1], ka.y, kb.y, kc.y, cu[1], cv[1]);
+        update_fast(ub[2], vb[2], ka.z, kb.z, kc.z, cu[2], cv[2]);
+        update_fast(ub[3], vb[3], ka.w, kb.w, kc.w, cu[3], cv[3]);
+    };
+
+    // ---- generic tick: pipeline fill, bottom-edge drain, tiny frames (runtime predicates) ----------
+    auto tick_gen = [&](const int r) {
         const int rr = r - base;                   // row relative to the first TMA group
         float cu[4], cv[4];
         bool have = false;
-        if (!GEN || r <= H - 1) {
+        if (r <= H - 1) {
             if ((rr % RG) == 0 || r == rs) {       // first row consumed from this group
                 const int gr = rr / RG;
                 mbar_wait(bar0 + 8u * (NGC + gr % NGUV), (gr / NGUV) & 1);
                 mbar_wait(bar0 + 8u * (gr % NGC), (gr / NGC) & 1);
             }
-            const int q = rr % NRUV;
-            const float4 tu = lds128(su + q * kStripW + lane * 4);
-            const float4 tv = lds128(sv + q * kStripW + lane * 4);
+            const int q = (rr % NRUV) * ROWB;
+            const float4 tu = *reinterpret_cast<const float4*>(su_l + q);
+            const float4 tv = *reinterpret_cast<const float4*>(su_l + UB + q);
             cu[0] = tu.x; cu[1] = tu.y; cu[2] = tu.z; cu[3] = tu.w;
             cv[0] = tv.x; cv[1] = tv.y; cv[2] = tv.z; cv[3] = tv.w;
             have = true;
@@ -183,13 +226,11 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
         for (int S = 0; S < T; ++S) {
             const int rho = r - S;                 // row of time step S this stage receives
             bool virt = false;
-            if (GEN) {
-                if (rho < rs || rho > H) have = false;
-                else if (rho == H) { virt = true; have = true; }   // row H == row H-1 (clamp)
-                if (!have) continue;
-            }
+            if (rho < rs || rho > H) have = false;
+            else if (rho == H) { virt = true; have = true; }   // row H == row H-1 (clamp)
+            if (!have) continue;
             float ub[4], vb[4];
-            if (GEN && virt) {
+            if (virt) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     ub[j] = combine<ST>(p[S][j], g[S][j]);
@@ -202,7 +243,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
                 if (edge) { clamp_lr(cu, col0, W, lu, ru); clamp_lr(cv, col0, W, lv, rv); }
                 const float hu[4] = {__fadd_rn(lu, cu[1]), __fadd_rn(cu[0], cu[2]), __fadd_rn(cu[1], cu[3]), __fadd_rn(cu[2], ru)};
                 const float hv[4] = {__fadd_rn(lv, cv[1]), __fadd_rn(cv[0], cv[2]), __fadd_rn(cv[1], cv[3]), __fadd_rn(cv[2], rv)};
-                if (GEN && rho == rs) {            // first row of this stage: replicate upwards
+                if (rho == rs) {                   // first row of this stage: replicate upwards
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float Gu = rowG<ST>(cu[j], hu[j]), Gv = rowG<ST>(cv[j], hv[j]);
@@ -222,10 +263,10 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
                 }
             }
             // time step S+1 of row rho-1 (coefficients of that row)
-            const int q = (rr - S - 1 + 2 * NRC) % NRC;
-            const float4 ka = lds128(sa + q * kStripW + lane * 4);
-            const float4 kb = lds128(sb + q * kStripW + lane * 4);
-            const float4 kc = lds128(sc + q * kStripW + lane * 4);
+            const int q = ((rr - S - 1 + 2 * NRC) % NRC) * ROWB;
+            const float4 ka = *reinterpret_cast<const float4*>(sa_l + q);
+            const float4 kb = *reinterpret_cast<const float4*>(sa_l + CB + q);
+            const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * CB + q);
             update_fast(ub[0], vb[0], ka.x, kb.x, kc.x, cu[0], cv[0]);
             update_fast(ub[1], vb[1], ka.y, kb.y, kc.y, cu[1], cv[1]);
             update_fast(ub[2], vb[2], ka.z, kb.z, kc.z, cu[2], cv[2]);
@@ -252,12 +293,70 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
         }
     };
 
+    // ---- steady state: one tick per trip, all T stages active, ring positions kept incrementally ----
+    float* uo_row = uo;                                         // advanced by one row per tick
+    float* vo_row = vo;
+    auto steady = [&](auto edge_tag, int r, const int r_end) {   // r group-aligned; returns the next tick
+        const int rr0 = r - base;
+        int grow = rr0 / RG;                                   // group of the current tick
+        int uoff = (rr0 % NRUV) * ROWB, coff = (rr0 % NRC) * ROWB;
+        int uslot = grow % NGUV, upar = (grow / NGUV) & 1, cslot = grow % NGC, cpar = (grow / NGC) & 1;
+        int gfin = (rr0 + RG - T) / RG - 1;                    // coefficient group retired when the current group ends (rr0 >= T here)
+        int phase = 0;                                         // tick inside the 2-row group
+        uo_row = uo + (size_t)(r - T) * A.row_pitch;
+        vo_row = vo + (size_t)(r - T) * A.row_pitch;
+#pragma unroll 1
+        for (; r <= r_end; ++r) {
+            if (phase == 0) {
+                mbar_wait(bar0 + 8u * (NGC + uslot), upar);
+                mbar_wait(bar0 + 8u * cslot, cpar);
+            }
+            float cu[4], cv[4];
+            const float4 tu = *reinterpret_cast<const float4*>(su_l + uoff);
+            const float4 tv = *reinterpret_cast<const float4*>(su_l + UB + uoff);
+            cu[0] = tu.x; cu[1] = tu.y; cu[2] = tu.z; cu[3] = tu.w;
+            cv[0] = tv.x; cv[1] = tv.y; cv[2] = tv.z; cv[3] = tv.w;
+            // stage S consumes row (r-S) and needs the coefficients of row (r-S-1)
+            [&]<int... S>(std::integer_sequence<int, S...>) {
+                (stage_row(edge_tag, std::integral_constant<int, S>{}, cu, cv, wrap_down<CB>(coff - (S + 1) * ROWB)), ...);
+            }(std::make_integer_sequence<int, T>{});
+            const int ro = r - T;
+            if (lane_out && ro >= R0 && ro < R1) {
+                *reinterpret_cast<float4*>(uo_row) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+                *reinterpret_cast<float4*>(vo_row) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            }
+            uo_row += A.row_pitch; vo_row += A.row_pitch;
+            uoff = wrap_up<UB>(uoff + ROWB);
+            coff = wrap_up<CB>(coff + ROWB);
+            if (++phase == RG) {
+                // this group's u/v rows are consumed and coefficient group `gfin` is retired: refill both slots
+                phase = 0;
+                __syncwarp();
+                if (lane == 0) {
+                    if (g0 + grow + NGUV <= glast) issue_uv(g0 + grow + NGUV);
+                    if (gfin >= 0 && g0 + gfin + NGC <= glast) issue_coef(g0 + gfin + NGC);
+                }
+                ++grow; ++gfin;
+                if (++uslot == NGUV) { uslot = 0; upar ^= 1; }
+                if (++cslot == NGC) { cslot = 0; cpar ^= 1; }
+            }
+        }
+        return r;
+    };
+
     int r = rs;
-    const int pro_end = min(rs + T, last_tick + 1);
-    for (; r < pro_end; ++r) tick(std::true_type{}, r);          // pipeline fill (and tiny frames)
-    const int steady_end = min(H - 1, last_tick);
-    for (; r <= steady_end; ++r) tick(std::false_type{}, r);     // all T stages active, no predicates
-    for (; r <= last_tick; ++r) tick(std::true_type{}, r);       // bottom edge: virtual rows
+    int gen_end = min(rs + T, last_tick + 1);                    // pipeline fill (and tiny frames)
+    gen_end += (RG - ((gen_end - base) % RG)) % RG;              // steady state starts group-aligned
+    gen_end = min(gen_end, last_tick + 1);
+    const int steady_end = min(H - 1, last_tick);                // last tick with a real input row
+    for (int pass = 0; pass < 2; ++pass) {
+        for (; r < gen_end; ++r) tick_gen(r);
+        if (pass == 1 || r > last_tick) break;
+        // whole groups only, so that the generic ticks that follow see consistent ring bookkeeping
+        const int st_end = r + ((steady_end - r + 1) / RG) * RG - 1;
+        r = edge ? steady(std::true_type{}, r, st_end) : steady(std::false_type{}, r, st_end);
+        gen_end = last_tick + 1;                                 // bottom edge / remainder: generic ticks
+    }
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -310,6 +409,23 @@ static cudaError_t launch_T(int st, const CUtensorMap& tu, const CUtensorMap& tv
                         : launch_one<T, ST_CV4>(tu, tv, ta, tb, tc, A, wpc, s);
 }
 
+template <int T> static int occ_T(int st, int wpc) {
+    using C = typename DefaultCfg<T>::type;
+    int n = 0;
+    const size_t smem = (size_t)wpc * C::SMEM_WARP;
+    cudaError_t e = st == ST_CL8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_jacobi_stream<T, ST_CL8>, wpc * 32, smem)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_jacobi_stream<T, ST_CV4>, wpc * 32, smem);
+    if (e != cudaSuccess) { cudaGetLastError(); return 8; }
+    return n * wpc;
+}
+int stream_warps_per_sm(int T, int stencil, int wpc) {
+    switch (T) {
+        case 1: return occ_T<1>(stencil, wpc); case 2: return occ_T<2>(stencil, wpc); case 3: return occ_T<3>(stencil, wpc);
+        case 4: return occ_T<4>(stencil, wpc); case 5: return occ_T<5>(stencil, wpc); case 6: return occ_T<6>(stencil, wpc);
+        case 7: return occ_T<7>(stencil, wpc); default: return occ_T<8>(stencil, wpc);
+    }
+}
+
 cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tu, const CUtensorMap& tv, const CUtensorMap& ta,
                                  const CUtensorMap& tb, const CUtensorMap& tc, StreamArgs A, int pairs, int wpc, cudaStream_t s) {
     const StreamGeom G = stream_geometry(T);
@@ -319,7 +435,7 @@ cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tu, cons
     A.ncy = (rows + A.chunk_rows - 1) / A.chunk_rows;
     A.total_units = (long long)A.nsx * A.ncy * pairs;
     if (wpc < 1) wpc = 1;
-    if (wpc > 8) wpc = 8;
+    if (wpc > 4) wpc = 4;
     while (wpc > 1 && (size_t)wpc * G.smem_per_warp > 227 * 1024) --wpc;
     switch (T) {
         case 1: return launch_T<1>(stencil, tu, tv, ta, tb, tc, A, wpc, s);

@@ -369,16 +369,24 @@ static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* 
     return HSFLOW_OK;
 }
 
-static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T) {
+// Rows per work unit.  Every unit re-computes 2T warm-up rows, and the launch ends with a partly
+// filled wave of resident warps: pick the chunk height that maximises
+//   chunk/(chunk + 2T)  x  units / (ceil(units/slots) x slots).
+static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T, int wpc) {
     if (h->chunk_rows > 0) return std::min(h->chunk_rows, rows);
-    // aim at >= ~16 work units per resident warp slot, chunks of at least 16*T rows
-    const long long slots = (long long)h->sm_count * 10;
-    const long long per_row_units = (long long)nsx * pairs;
-    long long want_chunks = (slots * 16 + per_row_units - 1) / per_row_units;
-    long long ch = rows / std::max<long long>(want_chunks, 1);
-    ch = std::max<long long>(ch, 16LL * T);
-    ch = std::min<long long>(ch, rows);
-    return (int)std::max<long long>(ch, 1);
+    const long long slots = (long long)h->sm_count * std::max(1, stream_warps_per_sm(T, h->stencil, wpc));
+    double best = -1.0;
+    int best_ch = rows;
+    for (int ncy = 1; ncy <= rows; ++ncy) {
+        const int ch = (rows + ncy - 1) / ncy;
+        if (ch < 4 * T && ncy > 1) break;
+        const long long units = (long long)nsx * ((rows + ch - 1) / ch) * pairs;
+        const long long waves = (units + slots - 1) / slots;
+        const double eff = (double)ch / (ch + 2.0 * T) * (double)units / (double)(waves * slots);
+        if (eff > best + 1e-9) { best = eff; best_ch = ch; }
+        if (ncy > 4096) break;
+    }
+    return best_ch;
 }
 
 // one launch advancing t iterations for n pairs.  src/dst: 0 = A planes (pair offset pA), 1 = B planes (offset 0)
@@ -393,10 +401,10 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
         const StreamGeom G = stream_geometry(t);
         const int nsx = (h->W + G.valid_w - 1) / G.valid_w;
-        A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, nsx, n, t);
         A.z_in0 = src == 0 ? pA : 0;
         A.z_c0 = 0;
-        const int wpc = h->wpc > 0 ? h->wpc : 4;
+        const int wpc = h->wpc > 0 ? std::min(h->wpc, 4) : 1;
+        A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, nsx, n, t, wpc);
         CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uA : h->tm_uB, src == 0 ? h->tm_vA : h->tm_vB,
                                 h->tm_c0, h->tm_c1, h->tm_c2, A, n, wpc, h->stream));
         h->launches++;
