@@ -220,6 +220,14 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = ALG_BYTES_PER_PX_IT * W4K * H4K * sub * (ITER / n_launch)
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
+    traffic = None                                # ncu dram bytes per launch, scaled from the committed capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            rec = json.load(f).get(f"k_jacobi_stream<T={T_eff}>")
+        if rec:
+            traffic = rec["dram_bytes_per_pixel_launch"] * W4K * H4K * sub
+    except Exception:
+        traffic = None
 
     # ---- e2e: pinned host frames in, u/v back to pinned host memory, every step ---------------------
     ep = min(args.e2e_pairs, pairs)
@@ -261,7 +269,7 @@ def run_ours(args, rank, world, local_rank):
                        "cache": "working set per step >> 126 MB L2 (no flush needed)"},
             "pairs_4k100_per_s": value * 1e6 / (W4K * H4K * ITER),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": f"k_jacobi_stream<T={T_eff}>", "launch_ms": launch_ms,
+                         "traffic": traffic, "kernel": f"k_jacobi_stream<T={T_eff}>", "launch_ms": launch_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "note": "unfused-equivalent bytes (28 B/px-it x T per launch): frac > 1 is the temporal-blocking gain; "
                                  "ncu dram bytes are in profiles/"},
@@ -300,7 +308,7 @@ def run_strip16k(args, rank, world, local_rank):
     eng.set_stream(stream.cuda_stream)
     eng.set_params(ALPHA, N, P.STENCIL_CL8, True, args.temporal_block)
     T = eng.temporal_block
-    ghost = args.ghost or T
+    ghost = args.ghost or 2 * T          # two temporal blocks per halo exchange
     solver = StripSolver(eng, W, H, rank, world, ghost, dist=dist)
     solver.load_synth(1234)
 
