@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) k_jacobi1(Jacobi1Args A) {
         const Row vp = load_row(vi, A.row_pitch, rho + 1, A.H, col0, A.W, lane);
         float4 k0 = make_float4(0, 0, 0, 0), k1 = k0, k2 = k0;
         if (inb) {
-            const size_t o = (size_t)rho * A.row_pitch + col0;
+            const size_t o = (size_t)rho * A.c_row_pitch + col0;
             k0 = __ldg(reinterpret_cast<const float4*>(c0 + o));
             k1 = __ldg(reinterpret_cast<const float4*>(c1 + o));
             k2 = __ldg(reinterpret_cast<const float4*>(c2 + o));

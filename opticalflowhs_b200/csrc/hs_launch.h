@@ -29,8 +29,9 @@ struct Jacobi1Args {
     const float* c0;
     const float* c1;
     const float* c2;
-    long long row_pitch;        // elements, common to all planes
-    long long in_pair_pitch, out_pair_pitch, c_pair_pitch;
+    long long row_pitch;        // elements, u/v planes (source and destination)
+    long long in_pair_pitch, out_pair_pitch;
+    long long c_row_pitch, c_pair_pitch;   // coefficient planes
     int W, H;                   // H = rows of the buffer (replicate beyond both ends)
     int out_lo, out_hi;         // rows to produce
     int chunk_rows;
@@ -69,9 +70,8 @@ constexpr int kStreamRowsPerBox = 2;   // TMA box = 128 columns x 2 rows
 StreamGeom stream_geometry(int T);
 cudaError_t stream_prepare(int device);     // opt in to large dynamic shared memory for every instantiation
 int stream_warps_per_sm(int T, int stencil, int warps_per_cta);   // resident warps per SM (occupancy API)
-// maps: u source, v source, coefficient planes a,b,c.  warps_per_cta in 1..4.
-cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tm_u, const CUtensorMap& tm_v,
-                                 const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_c,
+// maps: row-interleaved u/v source {W,2,H,pairs} and coefficients {W,3,H,pairs}.  warps_per_cta in 1..4.
+cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tm_uv, const CUtensorMap& tm_c,
                                  StreamArgs A, int pairs, int warps_per_cta, cudaStream_t s);
 
 }  // namespace hs

@@ -61,7 +61,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(bar)
         : "memory");
 }
-__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int x, int pl, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(pl), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
 
 // ---- geometry ------------------------------------------------------------------------------------
 template <int T, int RG, int NGC, int NGUV> struct StreamCfg {
@@ -70,7 +75,7 @@ template <int T, int RG, int NGC, int NGUV> struct StreamCfg {
     static constexpr int NRC = NGC * RG;                    // coefficient ring rows
     static constexpr int NRUV = NGUV * RG;                  // u/v ring rows
     static constexpr int ROWB = kStripW * 4;                // bytes per ring row
-    static constexpr int SMEM_WARP = (3 * NRC + 2 * NRUV) * ROWB + 128;   // + mbarriers
+    static constexpr int SMEM_WARP = (3 * NRC + 2 * NRUV) * ROWB + 128;   // coefficient ring + u/v ring + mbarriers
     // a coefficient group is refilled at the end of the RG-tick body that retires it; it must
     // have been issued at least one body before it is needed
     static_assert((NGC - 1) * RG >= T + 2, "coefficient ring too short for the stage lag");
@@ -84,7 +89,7 @@ template <int T> struct DefaultCfg {
     using type = StreamCfg<T, RG, NGC, NGUV>;
 };
 
-// ring offset arithmetic in bytes: power-of-two rings wrap with one AND
+// ring index arithmetic: power-of-two rings wrap with one AND
 template <int SIZE_BYTES> __device__ __forceinline__ int wrap_down(int off) {   // off in (-SIZE, SIZE)
     if ((SIZE_BYTES & (SIZE_BYTES - 1)) == 0) return off & (SIZE_BYTES - 1);
     return off < 0 ? off + SIZE_BYTES : off;
@@ -97,13 +102,13 @@ template <int SIZE_BYTES> __device__ __forceinline__ int wrap_up(int off) {     
 // ---- the kernel -----------------------------------------------------------------------------------
 template <int T, int ST>
 __global__ void __launch_bounds__(128)
-k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
-                const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                const __grid_constant__ CUtensorMap tm_c, const StreamArgs A) {
+k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant__ CUtensorMap tm_c, const StreamArgs A) {
     using C = typename DefaultCfg<T>::type;
     constexpr int RG = DefaultCfg<T>::RG, NGC = DefaultCfg<T>::NGC, NGUV = DefaultCfg<T>::NGUV;
     constexpr int NRC = C::NRC, NRUV = C::NRUV, ROWB = C::ROWB;
-    constexpr int CB = NRC * ROWB, UB = NRUV * ROWB;        // ring sizes in bytes
+    // rings are row-interleaved like the planes in HBM: a|b|c of one row are adjacent (CROW bytes), u|v likewise
+    constexpr int CROW = 3 * ROWB, UROW = 2 * ROWB;
+    constexpr int CB = NRC * CROW, UB = NRUV * UROW;        // ring sizes in bytes
     extern __shared__ __align__(128) uint8_t smem_raw[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,28 +132,23 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
     const bool wmis = (W & 3) != 0;
 
     uint8_t* wsm = smem_raw + (size_t)warp * C::SMEM_WARP;
-    // byte layout per warp: a ring | b ring | c ring | u ring | v ring | mbarriers
+    // byte layout per warp: coefficient ring | u/v ring | mbarriers
     const uint8_t* sa_l = wsm + lane * 16;                  // this lane's 16-byte column group
-    const uint8_t* su_l = wsm + 3 * CB + lane * 16;
-    const uint32_t sa32 = smem_u32(wsm), su32 = sa32 + 3 * CB;
-    const uint32_t bar0 = su32 + 2 * UB;                    // cbar[NGC] then uvbar[NGUV]
+    const uint8_t* su_l = wsm + CB + lane * 16;
+    const uint32_t sa32 = smem_u32(wsm), su32 = sa32 + CB;
+    const uint32_t bar0 = su32 + UB;                        // cbar[NGC] then uvbar[NGUV]
 
-    auto issue_coef = [&](int g) {                 // lane 0 only
+    auto issue_coef = [&](int g) {                 // lane 0 only: one box = RG rows x {a,b,c} x 128 columns
         const int slot = (g - g0) % NGC;
         const uint32_t bar = bar0 + 8u * slot;
-        mbar_expect_tx(bar, 3u * RG * ROWB);
-        const uint32_t off = (uint32_t)slot * RG * ROWB;
-        tma_load_3d(sa32 + off, &tm_a, x0, g * RG, A.z_c0 + z, bar);
-        tma_load_3d(sa32 + CB + off, &tm_b, x0, g * RG, A.z_c0 + z, bar);
-        tma_load_3d(sa32 + 2 * CB + off, &tm_c, x0, g * RG, A.z_c0 + z, bar);
+        mbar_expect_tx(bar, (uint32_t)RG * CROW);
+        tma_load_4d(sa32 + (uint32_t)slot * RG * CROW, &tm_c, x0, 0, g * RG, A.z_c0 + z, bar);
     };
-    auto issue_uv = [&](int g) {                   // lane 0 only
+    auto issue_uv = [&](int g) {                   // lane 0 only: one box = RG rows x {u,v} x 128 columns
         const int slot = (g - g0) % NGUV;
         const uint32_t bar = bar0 + 8u * (NGC + slot);
-        mbar_expect_tx(bar, 2u * RG * ROWB);
-        const uint32_t off = (uint32_t)slot * RG * ROWB;
-        tma_load_3d(su32 + off, &tm_u, x0, g * RG, A.z_in0 + z, bar);
-        tma_load_3d(su32 + UB + off, &tm_v, x0, g * RG, A.z_in0 + z, bar);
+        mbar_expect_tx(bar, (uint32_t)RG * UROW);
+        tma_load_4d(su32 + (uint32_t)slot * RG * UROW, &tm_uv, x0, 0, g * RG, A.z_in0 + z, bar);
     };
 
     if (lane == 0) {
@@ -185,8 +185,8 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
         float lv = __shfl_up_sync(kFull, cv[3], 1), rv = __shfl_down_sync(kFull, cv[0], 1);
         if (EDGE) { clamp_lr(cu, col0, W, lu, ru); clamp_lr(cv, col0, W, lv, rv); }
         const float4 ka = *reinterpret_cast<const float4*>(sa_l + coff);
-        const float4 kb = *reinterpret_cast<const float4*>(sa_l + CB + coff);
-        const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * CB + coff);
+        const float4 kb = *reinterpret_cast<const float4*>(sa_l + ROWB + coff);
+        const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * ROWB + coff);
         const float hu[4] = {__fadd_rn(lu, cu[1]), __fadd_rn(cu[0], cu[2]), __fadd_rn(cu[1], cu[3]), __fadd_rn(cu[2], ru)};
         const float hv[4] = {__fadd_rn(lv, cv[1]), __fadd_rn(cv[0], cv[2]), __fadd_rn(cv[1], cv[3]), __fadd_rn(cv[2], rv)};
         float ub[4], vb[4];
@@ -215,9 +215,9 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
                 mbar_wait(bar0 + 8u * (NGC + gr % NGUV), (gr / NGUV) & 1);
                 mbar_wait(bar0 + 8u * (gr % NGC), (gr / NGC) & 1);
             }
-            const int q = (rr % NRUV) * ROWB;
+            const int q = (rr % NRUV) * UROW;
             const float4 tu = *reinterpret_cast<const float4*>(su_l + q);
-            const float4 tv = *reinterpret_cast<const float4*>(su_l + UB + q);
+            const float4 tv = *reinterpret_cast<const float4*>(su_l + ROWB + q);
             cu[0] = tu.x; cu[1] = tu.y; cu[2] = tu.z; cu[3] = tu.w;
             cv[0] = tv.x; cv[1] = tv.y; cv[2] = tv.z; cv[3] = tv.w;
             have = true;
@@ -263,10 +263,10 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
                 }
             }
             // time step S+1 of row rho-1 (coefficients of that row)
-            const int q = ((rr - S - 1 + 2 * NRC) % NRC) * ROWB;
+            const int q = ((rr - S - 1 + 2 * NRC) % NRC) * CROW;
             const float4 ka = *reinterpret_cast<const float4*>(sa_l + q);
-            const float4 kb = *reinterpret_cast<const float4*>(sa_l + CB + q);
-            const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * CB + q);
+            const float4 kb = *reinterpret_cast<const float4*>(sa_l + ROWB + q);
+            const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * ROWB + q);
             update_fast(ub[0], vb[0], ka.x, kb.x, kc.x, cu[0], cv[0]);
             update_fast(ub[1], vb[1], ka.y, kb.y, kc.y, cu[1], cv[1]);
             update_fast(ub[2], vb[2], ka.z, kb.z, kc.z, cu[2], cv[2]);
@@ -299,7 +299,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
     auto steady = [&](auto edge_tag, int r, const int r_end) {   // r group-aligned; returns the next tick
         const int rr0 = r - base;
         int grow = rr0 / RG;                                   // group of the current tick
-        int uoff = (rr0 % NRUV) * ROWB, coff = (rr0 % NRC) * ROWB;
+        int urow = rr0 % NRUV, crow = rr0 % NRC;              // ring row of the current tick
         int uslot = grow % NGUV, upar = (grow / NGUV) & 1, cslot = grow % NGC, cpar = (grow / NGC) & 1;
         int gfin = (rr0 + RG - T) / RG - 1;                    // coefficient group retired when the current group ends (rr0 >= T here)
         int phase = 0;                                         // tick inside the 2-row group
@@ -312,13 +312,13 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
                 mbar_wait(bar0 + 8u * cslot, cpar);
             }
             float cu[4], cv[4];
-            const float4 tu = *reinterpret_cast<const float4*>(su_l + uoff);
-            const float4 tv = *reinterpret_cast<const float4*>(su_l + UB + uoff);
+            const float4 tu = *reinterpret_cast<const float4*>(su_l + urow * UROW);
+            const float4 tv = *reinterpret_cast<const float4*>(su_l + urow * UROW + ROWB);
             cu[0] = tu.x; cu[1] = tu.y; cu[2] = tu.z; cu[3] = tu.w;
             cv[0] = tv.x; cv[1] = tv.y; cv[2] = tv.z; cv[3] = tv.w;
             // stage S consumes row (r-S) and needs the coefficients of row (r-S-1)
             [&]<int... S>(std::integer_sequence<int, S...>) {
-                (stage_row(edge_tag, std::integral_constant<int, S>{}, cu, cv, wrap_down<CB>(coff - (S + 1) * ROWB)), ...);
+                (stage_row(edge_tag, std::integral_constant<int, S>{}, cu, cv, wrap_down<NRC>(crow - (S + 1)) * CROW), ...);
             }(std::make_integer_sequence<int, T>{});
             const int ro = r - T;
             if (lane_out && ro >= R0 && ro < R1) {
@@ -326,8 +326,8 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_u, const __grid_constant_
                 *reinterpret_cast<float4*>(vo_row) = make_float4(cv[0], cv[1], cv[2], cv[3]);
             }
             uo_row += A.row_pitch; vo_row += A.row_pitch;
-            uoff = wrap_up<UB>(uoff + ROWB);
-            coff = wrap_up<CB>(coff + ROWB);
+            urow = wrap_up<NRUV>(urow + 1);
+            crow = wrap_up<NRC>(crow + 1);
             if (++phase == RG) {
                 // this group's u/v rows are consumed and coefficient group `gfin` is retired: refill both slots
                 phase = 0;
@@ -392,21 +392,18 @@ cudaError_t stream_prepare(int) {
 }
 
 template <int T, int ST>
-static cudaError_t launch_one(const CUtensorMap& tu, const CUtensorMap& tv, const CUtensorMap& ta, const CUtensorMap& tb,
-                              const CUtensorMap& tc, const StreamArgs& A, int wpc, cudaStream_t s) {
+static cudaError_t launch_one(const CUtensorMap& tuv, const CUtensorMap& tc, const StreamArgs& A, int wpc, cudaStream_t s) {
     using C = typename DefaultCfg<T>::type;
     const size_t smem = (size_t)wpc * C::SMEM_WARP;
     const long long ctas = (A.total_units + wpc - 1) / wpc;
     if (ctas <= 0) return cudaSuccess;
     if (ctas > 0x7fffffffLL || smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    k_jacobi_stream<T, ST><<<(unsigned)ctas, wpc * 32, smem, s>>>(tu, tv, ta, tb, tc, A);
+    k_jacobi_stream<T, ST><<<(unsigned)ctas, wpc * 32, smem, s>>>(tuv, tc, A);
     return cudaGetLastError();
 }
 template <int T>
-static cudaError_t launch_T(int st, const CUtensorMap& tu, const CUtensorMap& tv, const CUtensorMap& ta, const CUtensorMap& tb,
-                            const CUtensorMap& tc, const StreamArgs& A, int wpc, cudaStream_t s) {
-    return st == ST_CL8 ? launch_one<T, ST_CL8>(tu, tv, ta, tb, tc, A, wpc, s)
-                        : launch_one<T, ST_CV4>(tu, tv, ta, tb, tc, A, wpc, s);
+static cudaError_t launch_T(int st, const CUtensorMap& tuv, const CUtensorMap& tc, const StreamArgs& A, int wpc, cudaStream_t s) {
+    return st == ST_CL8 ? launch_one<T, ST_CL8>(tuv, tc, A, wpc, s) : launch_one<T, ST_CV4>(tuv, tc, A, wpc, s);
 }
 
 template <int T> static int occ_T(int st, int wpc) {
@@ -426,8 +423,8 @@ int stream_warps_per_sm(int T, int stencil, int wpc) {
     }
 }
 
-cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tu, const CUtensorMap& tv, const CUtensorMap& ta,
-                                 const CUtensorMap& tb, const CUtensorMap& tc, StreamArgs A, int pairs, int wpc, cudaStream_t s) {
+cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tuv, const CUtensorMap& tc, StreamArgs A, int pairs,
+                                 int wpc, cudaStream_t s) {
     const StreamGeom G = stream_geometry(T);
     const int rows = A.out_hi - A.out_lo;
     if (rows <= 0 || pairs <= 0) return cudaSuccess;
@@ -438,14 +435,14 @@ cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tu, cons
     if (wpc > 4) wpc = 4;
     while (wpc > 1 && (size_t)wpc * G.smem_per_warp > 227 * 1024) --wpc;
     switch (T) {
-        case 1: return launch_T<1>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
-        case 2: return launch_T<2>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
-        case 3: return launch_T<3>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
-        case 4: return launch_T<4>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
-        case 5: return launch_T<5>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
-        case 6: return launch_T<6>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
-        case 7: return launch_T<7>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
-        case 8: return launch_T<8>(stencil, tu, tv, ta, tb, tc, A, wpc, s);
+        case 1: return launch_T<1>(stencil, tuv, tc, A, wpc, s);
+        case 2: return launch_T<2>(stencil, tuv, tc, A, wpc, s);
+        case 3: return launch_T<3>(stencil, tuv, tc, A, wpc, s);
+        case 4: return launch_T<4>(stencil, tuv, tc, A, wpc, s);
+        case 5: return launch_T<5>(stencil, tuv, tc, A, wpc, s);
+        case 6: return launch_T<6>(stencil, tuv, tc, A, wpc, s);
+        case 7: return launch_T<7>(stencil, tuv, tc, A, wpc, s);
+        case 8: return launch_T<8>(stencil, tuv, tc, A, wpc, s);
         default: return cudaErrorInvalidValue;
     }
 }

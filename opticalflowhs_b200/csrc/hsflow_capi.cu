@@ -54,7 +54,11 @@ struct hsflow {
     int W = 0, H = 0, P = 0, S = 0;
     int fmt = -1;
     long long f_row_pitch = 0, f_pair_pitch = 0;   // bytes
-    long long pitch = 0, ppair = 0;                // elements
+    // fp32 planes are ROW-INTERLEAVED: u and v rows alternate in one buffer ([pair][row][2][pitch]), the three
+    // coefficient planes likewise ([pair][row][3][pitch]).  One TMA box then fetches a row group of all planes.
+    long long pitch = 0;                           // elements of one plane row
+    long long uv_rp = 0, uv_pp = 0;                // u/v: row pitch (2*pitch) and pair pitch, elements
+    long long c_rp = 0, c_pp = 0;                  // coefficients: row pitch (3*pitch) and pair pitch, elements
     int top_edge = 1, bottom_edge = 1;
     // device memory
     uint8_t *f1 = nullptr, *f2 = nullptr, *fb1 = nullptr, *fb2 = nullptr;
@@ -63,7 +67,7 @@ struct hsflow {
     uint8_t* d_mask = nullptr;
     int* d_count = nullptr;
     size_t mask_cap = 0;
-    CUtensorMap tm_uA, tm_vA, tm_uB, tm_vB, tm_c0, tm_c1, tm_c2;
+    CUtensorMap tm_uvA, tm_uvB, tm_c;
     // state
     int cur = 0;                                   // 0: uA/vA hold the current field, 1: uB/vB
     int valid_lo = 0, valid_hi = 0;
@@ -75,8 +79,7 @@ struct hsflow {
 
 static void free_planes(hsflow* h) {
     cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2);
-    cudaFree(h->uA); cudaFree(h->vA); cudaFree(h->uB); cudaFree(h->vB);
-    cudaFree(h->c0); cudaFree(h->c1); cudaFree(h->c2); cudaFree(h->dtmp);
+    cudaFree(h->uA); cudaFree(h->uB); cudaFree(h->c0); cudaFree(h->dtmp);   // vA, vB, c1, c2 point into these
     h->f1 = h->f2 = h->fb1 = h->fb2 = nullptr;
     h->uA = h->vA = h->uB = h->vB = h->c0 = h->c1 = h->c2 = h->dtmp = nullptr;
     h->fmt = -1;
@@ -93,12 +96,14 @@ static bool use_stream_kernel(const hsflow* h, int t) {
     return t >= 2 || h->kernel_sel == 2;
 }
 
-static int make_map(hsflow* h, CUtensorMap* tm, float* base, int pairs) {
-    cuuint64_t dims[3] = {(cuuint64_t)h->W, (cuuint64_t)h->H, (cuuint64_t)pairs};
-    cuuint64_t strides[2] = {(cuuint64_t)h->pitch * 4, (cuuint64_t)h->ppair * 4};
-    cuuint32_t box[3] = {(cuuint32_t)kStripW, (cuuint32_t)kStreamRowsPerBox, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es,
+// 4-D map {W, planes, H, pairs} over a row-interleaved buffer; box = 128 columns x all planes x RG rows
+static int make_map(hsflow* h, CUtensorMap* tm, float* base, int planes, int pairs) {
+    cuuint64_t dims[4] = {(cuuint64_t)h->W, (cuuint64_t)planes, (cuuint64_t)h->H, (cuuint64_t)pairs};
+    cuuint64_t strides[3] = {(cuuint64_t)h->pitch * 4, (cuuint64_t)h->pitch * planes * 4,
+                             (cuuint64_t)h->pitch * planes * h->H * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kStripW, (cuuint32_t)planes, (cuuint32_t)kStreamRowsPerBox, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HSFLOW_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -236,26 +241,25 @@ int hsflow_configure(hsflow_t* h, int W, int H, int P) {
     h->W = W; h->H = H; h->P = P;
     h->S = h->sub_batch > 0 ? std::min(h->sub_batch, P) : std::min(P, 32);
     h->pitch = ((long long)W + 31) / 32 * 32;
-    h->ppair = h->pitch * H;
+    h->uv_rp = 2 * h->pitch; h->uv_pp = h->uv_rp * H;
+    h->c_rp = 3 * h->pitch; h->c_pp = h->c_rp * H;
     h->top_edge = h->bottom_edge = 1;
-    const size_t planeP = (size_t)h->ppair * P * sizeof(float), planeS = (size_t)h->ppair * h->S * sizeof(float);
-    if (cudaMalloc(&h->uA, planeP) != cudaSuccess || cudaMalloc(&h->vA, planeP) != cudaSuccess ||
-        cudaMalloc(&h->uB, planeS) != cudaSuccess || cudaMalloc(&h->vB, planeS) != cudaSuccess ||
-        cudaMalloc(&h->c0, planeS) != cudaSuccess || cudaMalloc(&h->c1, planeS) != cudaSuccess ||
-        cudaMalloc(&h->c2, planeS) != cudaSuccess) {
+    const size_t uvP = (size_t)h->uv_pp * P * sizeof(float), uvS = (size_t)h->uv_pp * h->S * sizeof(float);
+    const size_t cS = (size_t)h->c_pp * h->S * sizeof(float);
+    if (cudaMalloc(&h->uA, uvP) != cudaSuccess || cudaMalloc(&h->uB, uvS) != cudaSuccess ||
+        cudaMalloc(&h->c0, cS) != cudaSuccess) {
         cudaGetLastError();
         free_planes(h);
         h->W = h->H = h->P = 0;
         return fail(HSFLOW_ENOMEM, "cudaMalloc of %d x %d x %d planes failed", W, H, P);
     }
+    h->vA = h->uA + h->pitch; h->vB = h->uB + h->pitch;
+    h->c1 = h->c0 + h->pitch; h->c2 = h->c0 + 2 * h->pitch;
     int rc;
-    if ((rc = make_map(h, &h->tm_uA, h->uA, P)) || (rc = make_map(h, &h->tm_vA, h->vA, P)) ||
-        (rc = make_map(h, &h->tm_uB, h->uB, h->S)) || (rc = make_map(h, &h->tm_vB, h->vB, h->S)) ||
-        (rc = make_map(h, &h->tm_c0, h->c0, h->S)) || (rc = make_map(h, &h->tm_c1, h->c1, h->S)) ||
-        (rc = make_map(h, &h->tm_c2, h->c2, h->S)))
+    if ((rc = make_map(h, &h->tm_uvA, h->uA, 2, P)) || (rc = make_map(h, &h->tm_uvB, h->uB, 2, h->S)) ||
+        (rc = make_map(h, &h->tm_c, h->c0, 3, h->S)))
         return rc;
-    CK(cudaMemsetAsync(h->uA, 0, planeP, h->stream));
-    CK(cudaMemsetAsync(h->vA, 0, planeP, h->stream));
+    CK(cudaMemsetAsync(h->uA, 0, uvP, h->stream));
     h->cur = 0; h->valid_lo = 0; h->valid_hi = H;
     return HSFLOW_OK;
 }
@@ -339,11 +343,11 @@ int hsflow_load_pair_f32(hsflow_t* h, const float* f1, const float* f2, int w, i
 }
 
 // derivatives of pairs [p0, p0+n) into coefficient slots [0, n)
-static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* o1, float* o2) {
+static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* o1, float* o2, long long c_rp, long long c_pp) {
     DerivArgs A;
     A.f_row_pitch = h->f_row_pitch; A.f_pair_pitch = h->f_pair_pitch;
     A.c0 = o0; A.c1 = o1; A.c2 = o2;
-    A.c_row_pitch = h->pitch; A.c_pair_pitch = h->ppair;
+    A.c_row_pitch = c_rp; A.c_pair_pitch = c_pp;
     A.W = h->W; A.H = h->H; A.normalise = normalise; A.rho = h->rho;
     if (h->deriv == HSFLOW_DERIV_CL) {
         A.f1 = h->f1 + (size_t)p0 * h->f_pair_pitch;
@@ -391,13 +395,13 @@ static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T, 
 
 // one launch advancing t iterations for n pairs.  src/dst: 0 = A planes (pair offset pA), 1 = B planes (offset 0)
 static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int out_hi) {
-    float* uo = src == 0 ? h->uB : h->uA + (size_t)pA * h->ppair;
-    float* vo = src == 0 ? h->vB : h->vA + (size_t)pA * h->ppair;
+    float* uo = src == 0 ? h->uB : h->uA + (size_t)pA * h->uv_pp;
+    float* vo = src == 0 ? h->vB : h->vA + (size_t)pA * h->uv_pp;
     if (use_stream_kernel(h, t)) {
         StreamArgs A;
         memset(&A, 0, sizeof A);
         A.u_out = uo; A.v_out = vo;
-        A.row_pitch = h->pitch; A.out_pair_pitch = h->ppair;
+        A.row_pitch = h->uv_rp; A.out_pair_pitch = h->uv_pp;
         A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
         const StreamGeom G = stream_geometry(t);
         const int nsx = (h->W + G.valid_w - 1) / G.valid_w;
@@ -405,19 +409,19 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         A.z_c0 = 0;
         const int wpc = h->wpc > 0 ? std::min(h->wpc, 4) : 1;
         A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, nsx, n, t, wpc);
-        CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uA : h->tm_uB, src == 0 ? h->tm_vA : h->tm_vB,
-                                h->tm_c0, h->tm_c1, h->tm_c2, A, n, wpc, h->stream));
+        CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uvA : h->tm_uvB, h->tm_c, A, n, wpc, h->stream));
         h->launches++;
         return HSFLOW_OK;
     }
     if (t != 1) return fail(HSFLOW_EINVAL, "internal: single-sweep kernel advances one iteration per launch");
     Jacobi1Args A;
     memset(&A, 0, sizeof A);
-    A.u_in = src == 0 ? h->uA + (size_t)pA * h->ppair : h->uB;
-    A.v_in = src == 0 ? h->vA + (size_t)pA * h->ppair : h->vB;
+    A.u_in = src == 0 ? h->uA + (size_t)pA * h->uv_pp : h->uB;
+    A.v_in = src == 0 ? h->vA + (size_t)pA * h->uv_pp : h->vB;
     A.u_out = uo; A.v_out = vo;
     A.c0 = h->c0; A.c1 = h->c1; A.c2 = h->c2;
-    A.row_pitch = h->pitch; A.in_pair_pitch = A.out_pair_pitch = A.c_pair_pitch = h->ppair;
+    A.row_pitch = h->uv_rp; A.in_pair_pitch = A.out_pair_pitch = h->uv_pp;
+    A.c_row_pitch = h->c_rp; A.c_pair_pitch = h->c_pp;
     A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
     A.chunk_rows = h->chunk_rows > 0 ? h->chunk_rows : std::max(1, std::min(out_hi - out_lo, 64));
     A.rho = h->rho;
@@ -433,14 +437,12 @@ int hsflow_prepare(hsflow_t* h) {
     CK(cudaSetDevice(h->device));
     phase_begin(h, HSFLOW_PHASE_DERIV);
     const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
-    int rc = run_deriv(h, 0, h->P, norm, h->c0, h->c1, h->c2);
+    int rc = run_deriv(h, 0, h->P, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp);
     if (rc) return rc;
     h->coef_norm = norm;
     if (!h->warm) {                                // cpp:331-332: u, v start at zero for every pair
-        float* u = h->cur == 0 ? h->uA : h->uB;
-        float* v = h->cur == 0 ? h->vA : h->vB;
-        CK(cudaMemsetAsync(u, 0, (size_t)h->ppair * h->P * sizeof(float), h->stream));
-        CK(cudaMemsetAsync(v, 0, (size_t)h->ppair * h->P * sizeof(float), h->stream));
+        float* uv = h->cur == 0 ? h->uA : h->uB;             // u and v rows share the buffer
+        CK(cudaMemsetAsync(uv, 0, (size_t)h->uv_pp * h->P * sizeof(float), h->stream));
     }
     phase_end(h, HSFLOW_PHASE_DERIV);
     h->valid_lo = 0; h->valid_hi = h->H;
@@ -491,14 +493,12 @@ static int compute_subbatch(hsflow* h, int p0, int n) {
     for (int left = N; left > 0;) { const int t = std::min(left, T); L += use_stream_kernel(h, t) ? 1 : t; left -= t; }
     (void)streamk;
     const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
-    int rc = run_deriv(h, p0, n, norm, h->c0, h->c1, h->c2);
+    int rc = run_deriv(h, p0, n, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp);
     if (rc) return rc;
     h->coef_norm = norm;
     int src = (L % 2 == 0) ? 0 : 1;                // so that the last flip lands in A
-    float* u = src == 0 ? h->uA + (size_t)p0 * h->ppair : h->uB;
-    float* v = src == 0 ? h->vA + (size_t)p0 * h->ppair : h->vB;
-    CK(cudaMemsetAsync(u, 0, (size_t)h->ppair * n * sizeof(float), h->stream));   // cpp:331-332
-    CK(cudaMemsetAsync(v, 0, (size_t)h->ppair * n * sizeof(float), h->stream));
+    float* uv = src == 0 ? h->uA + (size_t)p0 * h->uv_pp : h->uB;
+    CK(cudaMemsetAsync(uv, 0, (size_t)h->uv_pp * n * sizeof(float), h->stream));   // cpp:331-332
     for (int left = N; left > 0;) {
         const int t = std::min(left, T);
         if (use_stream_kernel(h, t)) {
@@ -552,8 +552,8 @@ int hsflow_read_uv(hsflow_t* h, int pair, float* u, float* v, size_t pitch) {
     if (pitch == 0) pitch = wb;
     if (pitch < wb) return fail(HSFLOW_EINVAL, "pitch too small");
     phase_begin(h, HSFLOW_PHASE_READ);
-    if (u) CK(cudaMemcpy2DAsync(u, pitch, cur_u(h) + (size_t)pair * h->ppair, h->pitch * sizeof(float), wb, h->H, cudaMemcpyDeviceToHost, h->stream));
-    if (v) CK(cudaMemcpy2DAsync(v, pitch, cur_v(h) + (size_t)pair * h->ppair, h->pitch * sizeof(float), wb, h->H, cudaMemcpyDeviceToHost, h->stream));
+    if (u) CK(cudaMemcpy2DAsync(u, pitch, cur_u(h) + (size_t)pair * h->uv_pp, h->uv_rp * sizeof(float), wb, h->H, cudaMemcpyDeviceToHost, h->stream));
+    if (v) CK(cudaMemcpy2DAsync(v, pitch, cur_v(h) + (size_t)pair * h->uv_pp, h->uv_rp * sizeof(float), wb, h->H, cudaMemcpyDeviceToHost, h->stream));
     phase_end(h, HSFLOW_PHASE_READ);
     CK(cudaStreamSynchronize(h->stream));
     return HSFLOW_OK;
@@ -564,8 +564,8 @@ int hsflow_write_uv(hsflow_t* h, int pair, const float* u, const float* v, size_
     if (pair < 0 || pair >= h->P || (h->cur == 1 && pair >= h->S)) return fail(HSFLOW_EINVAL, "pair %d out of range", pair);
     const size_t wb = (size_t)h->W * sizeof(float);
     if (pitch == 0) pitch = wb;
-    if (u) CK(cudaMemcpy2DAsync(cur_u(h) + (size_t)pair * h->ppair, h->pitch * sizeof(float), u, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
-    if (v) CK(cudaMemcpy2DAsync(cur_v(h) + (size_t)pair * h->ppair, h->pitch * sizeof(float), v, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
+    if (u) CK(cudaMemcpy2DAsync(cur_u(h) + (size_t)pair * h->uv_pp, h->uv_rp * sizeof(float), u, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
+    if (v) CK(cudaMemcpy2DAsync(cur_v(h) + (size_t)pair * h->uv_pp, h->uv_rp * sizeof(float), v, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return HSFLOW_OK;
 }
@@ -575,12 +575,13 @@ int hsflow_read_derivatives(hsflow_t* h, int pair, float* Ex, float* Ey, float* 
     if (pair < 0 || pair >= h->P || !h->f1) return fail(HSFLOW_EINVAL, "pair %d out of range or no frames", pair);
     const size_t wb = (size_t)h->W * sizeof(float);
     if (pitch == 0) pitch = wb;
-    if (!h->dtmp && cudaMalloc(&h->dtmp, 3 * (size_t)h->ppair * sizeof(float)) != cudaSuccess) {
+    const long long plane = h->pitch * h->H;
+    if (!h->dtmp && cudaMalloc(&h->dtmp, 3 * (size_t)plane * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
         return fail(HSFLOW_ENOMEM, "cudaMalloc");
     }
-    float* d[3] = {h->dtmp, h->dtmp + h->ppair, h->dtmp + 2 * h->ppair};
-    int rc = run_deriv(h, pair, 1, 0, d[0], d[1], d[2]);
+    float* d[3] = {h->dtmp, h->dtmp + plane, h->dtmp + 2 * plane};
+    int rc = run_deriv(h, pair, 1, 0, d[0], d[1], d[2], h->pitch, plane);
     if (rc) return rc;
     float* o[3] = {Ex, Ey, Et};
     for (int k = 0; k < 3; ++k)
@@ -594,8 +595,8 @@ int hsflow_get_device_uv(hsflow_t* h, float** u, float** v, size_t* row_pitch, s
     if (!h->uA) return fail(HSFLOW_EINVAL, "not configured");
     if (u) *u = cur_u(h);
     if (v) *v = cur_v(h);
-    if (row_pitch) *row_pitch = (size_t)h->pitch;
-    if (pair_pitch) *pair_pitch = (size_t)h->ppair;
+    if (row_pitch) *row_pitch = (size_t)h->uv_rp;       // v == u + row_pitch/2: u and v rows interleave
+    if (pair_pitch) *pair_pitch = (size_t)h->uv_pp;
     return HSFLOW_OK;
 }
 int hsflow_get_device_frames(hsflow_t* h, uint8_t** f1, uint8_t** f2, size_t* row_pitch, size_t* pair_pitch) {
@@ -621,7 +622,7 @@ int hsflow_dot_mask(hsflow_t* h, int pair, int step, float thr, uint8_t* mask, i
         h->mask_cap = need;
     }
     CK(cudaMemsetAsync(h->d_count, 0, sizeof(int), h->stream));
-    CK(launch_dot_mask(cur_u(h) + (size_t)pair * h->ppair, cur_v(h) + (size_t)pair * h->ppair, h->W, h->H, h->pitch, step, thr,
+    CK(launch_dot_mask(cur_u(h) + (size_t)pair * h->uv_pp, cur_v(h) + (size_t)pair * h->uv_pp, h->W, h->H, h->uv_rp, step, thr,
                        h->d_mask, h->d_count, h->stream));
     h->launches++;
     CK(cudaMemcpyAsync(mask, h->d_mask, need, cudaMemcpyDeviceToHost, h->stream));
@@ -680,8 +681,8 @@ int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w
         CK(cudaEventRecord(ev_comp[slot], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, ev_comp[slot], 0));
         for (int k = 0; k < n; ++k) {
-            CK(cudaMemcpy2DAsync(u_out + (size_t)(first + k) * px, wb, h->uA + (size_t)(p0 + k) * h->ppair, h->pitch * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
-            CK(cudaMemcpy2DAsync(v_out + (size_t)(first + k) * px, wb, h->vA + (size_t)(p0 + k) * h->ppair, h->pitch * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
+            CK(cudaMemcpy2DAsync(u_out + (size_t)(first + k) * px, wb, h->uA + (size_t)(p0 + k) * h->uv_pp, h->uv_rp * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
+            CK(cudaMemcpy2DAsync(v_out + (size_t)(first + k) * px, wb, h->vA + (size_t)(p0 + k) * h->uv_pp, h->uv_rp * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
         }
         CK(cudaEventRecord(ev_out[slot], h->s_out));
     }

@@ -13,7 +13,8 @@ One process per GPU (torchrun), `torch.distributed` only for plumbing:
                       same operation sequence.
 
 The solver talks to an engine object with the HSFlow method set (configure, set_strip,
-set_frames / synth_frames, prepare, iterate, halo_refreshed, uv_tensors); the CPU test-suite
+set_frames / synth_frames, prepare, iterate, halo_refreshed) plus a callable returning the flow
+planes as a list of [rows, n] torch tensors; the CPU test-suite
 plugs a numpy stand-in into the same exchange code under the gloo backend.
 """
 import math
@@ -76,13 +77,14 @@ class DeviceView:
 
 
 def engine_uv_tensors(engine, device_index):
-    """Current u/v planes of an HSFlow handle as torch tensors [rows, pitch] (no copy)."""
+    """Current flow planes of an HSFlow handle as torch tensors over device memory (no copy).
+
+    The engine keeps u and v row-interleaved in ONE buffer ([row][u|v][pitch]), so a block of rows of
+    the returned [rows, 2*pitch] tensor carries both fields and one send per seam and direction is enough."""
     import torch
-    u, v, rp, _ = engine.device_uv()
+    u, _, rp, _ = engine.device_uv()
     dev = torch.device("cuda", device_index)
-    tu = torch.as_tensor(DeviceView(u, (engine.H, rp)), device=dev)
-    tv = torch.as_tensor(DeviceView(v, (engine.H, rp)), device=dev)
-    return tu, tv
+    return [torch.as_tensor(DeviceView(u, (engine.H, rp)), device=dev)]
 
 
 class StripSolver:
@@ -111,9 +113,8 @@ class StripSolver:
         p, g = self.plan, self.plan.ghost
         if p.world > 1:
             dist = self.dist
-            tu, tv = self._uv()
             ops = []
-            for t in (tu, tv):
+            for t in self._uv():      # one [rows, 2*pitch] tensor on the GPU engine, [u, v] on the CPU stand-in
                 if not p.is_top:      # upper neighbour's bottom ghost holds g+1 rows; my top ghost holds g rows
                     ops.append(dist.P2POp(dist.isend, t[p.top_ghost:p.top_ghost + g + 1], p.rank - 1))
                     ops.append(dist.P2POp(dist.irecv, t[0:p.top_ghost], p.rank - 1))

@@ -57,4 +57,4 @@ class NumpyEngine:
         return self
 
     def uv_tensors(self):
-        return torch.from_numpy(self.u), torch.from_numpy(self.v)
+        return [torch.from_numpy(self.u), torch.from_numpy(self.v)]
