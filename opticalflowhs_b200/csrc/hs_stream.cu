@@ -6,11 +6,11 @@
 //
 // Design (B200-first, HBM-bound fp32 stencil -- no tensor cores on purpose):
 //  * work unit = one WARP x (128-column strip, row chunk, frame pair).  Warps are autonomous:
-//    own shared-memory rings, own mbarriers, no __syncthreads anywhere.
-//  * TMA (cp.async.bulk.tensor.3d, one elected lane) stages 128 x RG row boxes of u, v
-//    (source planes) and a, b, c (normalised coefficients) into per-warp rings; out-of-image
-//    columns are zero-filled by the TMA unit and then re-clamped in registers (Neumann border,
-//    Tex2D Kernels.cl:2-9), so the kernel has no bounds checks on loads.
+//    own shared-memory rings, own mbarriers, no __syncthreads anywhere; one warp per CTA by default.
+//  * the fp32 planes are row-interleaved in HBM ([row][u|v][pitch], [row][a|b|c][pitch]), so ONE TMA
+//    operation (cp.async.bulk.tensor.4d, box = 128 columns x all planes x 2 rows, issued by one
+//    elected lane) refills a ring slot.  Out-of-image columns are zero-filled by the TMA unit and
+//    re-clamped in registers (Neumann border, Tex2D Kernels.cl:2-9): no bounds checks on loads.
 //  * the warp streams DOWN the rows.  Each lane owns 4 adjacent columns.  Time step s+1 of row
 //    r-1 is produced as soon as time step s of row r exists, so T time steps are in flight as a
 //    register pipeline: per stage and field only two partial sums per pixel are kept
@@ -18,10 +18,14 @@
 //  * left/right neighbours come from warp shuffles (one __shfl_up + one __shfl_down per field
 //    and stage-row); the strip carries a halo of HL >= T columns on each side that absorbs the
 //    shrinking valid region, the chunk carries T warm-up rows above and below.
+//  * three code paths: a generic tick with run-time predicates (pipeline fill, bottom-edge drain,
+//    tiny frames) and two branch-free steady-state loops (interior strips / strips touching the
+//    left or right image edge), two ticks = one TMA row group per trip, ring positions and
+//    barrier phases kept incrementally.
 //  * results leave through coalesced 16-byte stores of the strip's valid columns.
 // Per pixel-iteration: 14 FP32 instructions, 1 shuffle, 12 B of shared-memory reads; HBM
-// traffic 28 B / T per pixel-iteration (+ halo overhead).  tests/stream_model.py is the numpy
-// model of exactly this bookkeeping.
+// traffic 28 B / T per pixel-iteration (+ halo overhead; measured 29 B per pixel and launch at T=4).
+// tests/stream_model.py is the numpy model of exactly this bookkeeping.
 #include <type_traits>
 #include <utility>
 
@@ -305,6 +309,46 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         int phase = 0;                                         // tick inside the 2-row group
         uo_row = uo + (size_t)(r - T) * A.row_pitch;
         vo_row = vo + (size_t)(r - T) * A.row_pitch;
+#ifndef HS_STREAM_UNROLL2
+#define HS_STREAM_UNROLL2 1
+#endif
+#if HS_STREAM_UNROLL2
+        // two ticks (= one TMA row group) per trip: the p/g rotation needs no register moves
+        (void)phase;
+#pragma unroll 1
+        for (; r + RG - 1 <= r_end; r += RG) {
+            mbar_wait(bar0 + 8u * (NGC + uslot), upar);
+            mbar_wait(bar0 + 8u * cslot, cpar);
+#pragma unroll
+            for (int j = 0; j < RG; ++j) {
+                float cu[4], cv[4];
+                const int ur = wrap_up<NRUV>(urow + j), cr = wrap_up<NRC>(crow + j);
+                const float4 tu = *reinterpret_cast<const float4*>(su_l + ur * UROW);
+                const float4 tv = *reinterpret_cast<const float4*>(su_l + ur * UROW + ROWB);
+                cu[0] = tu.x; cu[1] = tu.y; cu[2] = tu.z; cu[3] = tu.w;
+                cv[0] = tv.x; cv[1] = tv.y; cv[2] = tv.z; cv[3] = tv.w;
+                [&]<int... S>(std::integer_sequence<int, S...>) {
+                    (stage_row(edge_tag, std::integral_constant<int, S>{}, cu, cv, wrap_down<NRC>(cr - (S + 1)) * CROW), ...);
+                }(std::make_integer_sequence<int, T>{});
+                const int ro = r + j - T;
+                if (lane_out && ro >= R0 && ro < R1) {
+                    *reinterpret_cast<float4*>(uo_row) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+                    *reinterpret_cast<float4*>(vo_row) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                }
+                uo_row += A.row_pitch; vo_row += A.row_pitch;
+            }
+            urow = wrap_up<NRUV>(urow + RG);
+            crow = wrap_up<NRC>(crow + RG);
+            __syncwarp();
+            if (lane == 0) {
+                if (g0 + grow + NGUV <= glast) issue_uv(g0 + grow + NGUV);
+                if (gfin >= 0 && g0 + gfin + NGC <= glast) issue_coef(g0 + gfin + NGC);
+            }
+            ++grow; ++gfin;
+            if (++uslot == NGUV) { uslot = 0; upar ^= 1; }
+            if (++cslot == NGC) { cslot = 0; cpar ^= 1; }
+        }
+#else
 #pragma unroll 1
         for (; r <= r_end; ++r) {
             if (phase == 0) {
@@ -341,6 +385,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
                 if (++cslot == NGC) { cslot = 0; cpar ^= 1; }
             }
         }
+#endif
         return r;
     };
 

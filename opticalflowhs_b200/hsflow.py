@@ -12,7 +12,7 @@ DERIV_CL, DERIV_CV = 0, 1
 PHASE_LOAD, PHASE_DERIV, PHASE_ITER, PHASE_READ = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "libhsflow.so")
+_LIBPATH = os.environ.get("HSFLOW_LIBRARY") or os.path.join(_HERE, "libhsflow.so")   # override: A/B kernel experiments
 _lib = None
 
 
