@@ -308,8 +308,10 @@ def run_strip16k(args, rank, world, local_rank):
     eng.set_stream(stream.cuda_stream)
     eng.set_params(ALPHA, N, P.STENCIL_CL8, True, args.temporal_block)
     T = eng.temporal_block
-    ghost = args.ghost or 2 * T          # two temporal blocks per halo exchange
-    solver = StripSolver(eng, W, H, rank, world, ghost, dist=dist)
+    transport = args.transport if world > 1 else "none"
+    # p2p: the kernel pushes seam rows every launch (ghost = T); nccl: two temporal blocks per halo exchange
+    ghost = args.ghost or (T if transport == "p2p" else 2 * T)
+    solver = StripSolver(eng, W, H, rank, world, ghost, dist=dist, transport=args.transport)
     solver.load_synth(1234)
 
     def barrier():
@@ -344,14 +346,16 @@ def run_strip16k(args, rank, world, local_rank):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"synthetic {W}x{H} single frame pair, alpha={ALPHA:g}, {N} iterations, FULL mode, "
-                                   f"row strips over {world} GPU(s) with halo exchange every {ghost} iterations "
-                                   "(BASELINE.json configs[4])", "temporal_block": T, "ghost_rows": ghost,
+                                   f"row strips over {world} GPU(s), seam transport {transport} "
+                                   f"({'seam rows stored into the neighbours by the iteration kernel every launch' if transport == 'p2p' else f'halo exchange every {ghost} iterations'}) "
+                                   "(BASELINE.json configs[4])", "temporal_block": T, "ghost_rows": ghost, "transport": transport,
                        "halo_bytes_sent_per_exchange": solver.plan.halo_bytes_per_exchange(W), "exchanges": solver.exchanges},
             "roofline": {"bound": "hbm", "achieved": value * 1e6 * ALG_BYTES_PER_PX_IT / 1e9 / world, "peak": peak,
                          "unit": "GB/s", "frac": value * 1e6 * ALG_BYTES_PER_PX_IT / 1e9 / world / peak, "traffic": None,
                          "peak_source": peak_src, "note": "per-GPU unfused-equivalent bandwidth of the whole strip job"},
             "ideal_ms_at_hbm_peak": 1e3 * ideal_strip_time_s(W, H, N, world, peak),
             "gpu_launches": int(launches), "clocks": clocks}), flush=True)
+    solver.close()
     eng.close()
     if dist:
         dist.barrier()
@@ -409,6 +413,8 @@ def main():
                          "row-strip sharded with NVLink halo exchange; sweep1080p: configs[2], temporal-block sweep")
     ap.add_argument("--pairs", type=int, default=256, help="4K frame pairs per GPU and step")
     ap.add_argument("--ghost", type=int, default=0, help="strip16k: ghost rows per seam = iterations per halo exchange (0: = T)")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="strip16k: p2p = seam rows pushed by the iteration kernel over NVLink peer memory; nccl = send/recv")
     ap.add_argument("--iterations", type=int, default=0, help="strip16k / sweep1080p: override the iteration count")
     ap.add_argument("--e2e-pairs", type=int, default=64)
     ap.add_argument("--temporal-block", type=int, default=0)

@@ -112,6 +112,24 @@ int hsflow_iterate(hsflow_t* h, int n);     /* n x runCLKernels (cpp:476-679)   
 int hsflow_halo_refreshed(hsflow_t* h);
 int hsflow_sync(hsflow_t* h);
 
+/* ---- row strips with PEER transport (BASELINE.json north_star: "halo exchange over NVLink via ... P2P stores").
+ * The reference keeps the whole frame on one device (cpp:158 devices[0]); this is the multi-GPU form of
+ * runCLKernels (cpp:476-679) for one very large frame.  Each strip publishes an opaque handle
+ * (CUDA IPC handles of its two u/v buffers and of its signal words; plain pointers for strips living in
+ * the same process); the caller carries the handles to the neighbours (any transport: torch.distributed
+ * object all-gather, a pipe, shared memory) and connects.  From then on hsflow_iterate() needs no halo
+ * call at all: the iteration kernel stores rows [lo, hi) of its output ALSO into the neighbour's buffer at
+ * row + delta over NVLink, and the last thread block to finish publishes an epoch number in the
+ * neighbours' signal words; each strip's stream waits on its own words (cuStreamWaitValue32) between
+ * launches.  Ghost rows per seam must be >= the temporal block.  All strips must issue the same sequence
+ * of prepare/iterate calls.  NULL handle = no neighbour on that side (true image edge). */
+typedef struct hsflow_strip_handle { unsigned char opaque[320]; } hsflow_strip_handle_t;
+int hsflow_strip_export(hsflow_t* h, hsflow_strip_handle_t* out);
+int hsflow_strip_connect(hsflow_t* h,
+                         const hsflow_strip_handle_t* up, int up_row_lo, int up_row_hi, int up_row_delta,
+                         const hsflow_strip_handle_t* down, int down_row_lo, int down_row_hi, int down_row_delta);
+int hsflow_strip_disconnect(hsflow_t* h);   /* call on every strip before any of them is reconfigured or destroyed */
+
 /* ---- results: replaces clEnqueueReadBuffer of u,v (cpp:655-675) / Ex,Ey,Et (cpp:437-468) - */
 int hsflow_read_uv(hsflow_t* h, int pair, float* u, float* v, size_t pitch);              /* sync */
 int hsflow_read_derivatives(hsflow_t* h, int pair, float* Ex, float* Ey, float* Et, size_t pitch); /* sync */

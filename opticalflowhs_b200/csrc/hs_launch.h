@@ -49,6 +49,18 @@ struct StreamArgs {
     int nsx, ncy;
     int z_in0, z_c0;            // first pair index inside the u/v source map and the coefficient maps
     long long total_units;
+    // Row-strip mode with peer transport (hsflow_strip_connect): output rows [up_lo, up_hi) are ALSO stored into the
+    // upper neighbour's destination buffer at row + up_delta (its bottom ghost rows), rows [dn_lo, dn_hi) into the
+    // lower neighbour's at row + dn_delta (its top ghost rows), over NVLink peer memory.  The last work unit of the
+    // launch to finish publishes `epoch` in both neighbours' flag words (fused compute + halo exchange + signal).
+    float* peer_up;             // neighbour buffers (u plane; v = u + (v_out - u_out)), nullptr: no neighbour
+    float* peer_dn;
+    int up_lo, up_hi, up_delta;
+    int dn_lo, dn_hi, dn_delta;
+    unsigned* done_counter;     // device word, 0 between launches; nullptr: no signalling
+    unsigned* flag_up;          // word in the upper / lower neighbour's memory that receives `epoch`
+    unsigned* flag_dn;
+    unsigned epoch;
 };
 
 struct StreamGeom {             // filled by stream_geometry()

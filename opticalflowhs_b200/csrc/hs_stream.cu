@@ -179,6 +179,26 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     float* uo = A.u_out + (size_t)z * A.out_pair_pitch + col0;
     float* vo = A.v_out + (size_t)z * A.out_pair_pitch + col0;
 
+    // Peer transport (row strips over several GPUs): rows a neighbour keeps as ghost rows are stored a second time,
+    // straight into that neighbour's destination buffer over NVLink.  Decided per chunk: only the units at the top
+    // and bottom of the strip ever take the branch.
+    const bool push_up = A.peer_up != nullptr && R0 < A.up_hi && R1 > A.up_lo;
+    const bool push_dn = A.peer_dn != nullptr && R0 < A.dn_hi && R1 > A.dn_lo;
+    const bool push_any = push_up || push_dn;
+    const long long voff = A.v_out - A.u_out;
+    auto push_row = [&](const int ro, const float (&cu)[4], const float (&cv)[4]) {
+        if (push_up && ro >= A.up_lo && ro < A.up_hi) {
+            float* q = A.peer_up + (size_t)(ro + A.up_delta) * A.row_pitch + col0;
+            *reinterpret_cast<float4*>(q) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+            *reinterpret_cast<float4*>(q + voff) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        }
+        if (push_dn && ro >= A.dn_lo && ro < A.dn_hi) {
+            float* q = A.peer_dn + (size_t)(ro + A.dn_delta) * A.row_pitch + col0;
+            *reinterpret_cast<float4*>(q) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+            *reinterpret_cast<float4*>(q + voff) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        }
+    };
+
     // one stage-row in steady state: time step S of one row (cu, cv) -> time step S+1 of the row
     // above it, written back into cu, cv.  coff = byte offset of that row's coefficients.
     auto stage_row = [&](auto edge_tag, auto s_tag, float (&cu)[4], float (&cv)[4], const int coff) {
@@ -281,6 +301,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             const size_t o = (size_t)ro * A.row_pitch;
             *reinterpret_cast<float4*>(uo + o) = make_float4(cu[0], cu[1], cu[2], cu[3]);
             *reinterpret_cast<float4*>(vo + o) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+            if (push_any) push_row(ro, cu, cv);
         }
         // Ring refills, after every lane consumed its shared-memory reads of this tick:
         //  * the u/v group whose last row was read by stage 0 in this tick,
@@ -334,6 +355,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
                 if (lane_out && ro >= R0 && ro < R1) {
                     *reinterpret_cast<float4*>(uo_row) = make_float4(cu[0], cu[1], cu[2], cu[3]);
                     *reinterpret_cast<float4*>(vo_row) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                    if (push_any) push_row(ro, cu, cv);
                 }
                 uo_row += A.row_pitch; vo_row += A.row_pitch;
             }
@@ -368,6 +390,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             if (lane_out && ro >= R0 && ro < R1) {
                 *reinterpret_cast<float4*>(uo_row) = make_float4(cu[0], cu[1], cu[2], cu[3]);
                 *reinterpret_cast<float4*>(vo_row) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                if (push_any) push_row(ro, cu, cv);
             }
             uo_row += A.row_pitch; vo_row += A.row_pitch;
             urow = wrap_up<NRUV>(urow + 1);
@@ -401,6 +424,23 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         const int st_end = r + ((steady_end - r + 1) / RG) * RG - 1;
         r = edge ? steady(std::true_type{}, r, st_end) : steady(std::false_type{}, r, st_end);
         gen_end = last_tick + 1;                                 // bottom edge / remainder: generic ticks
+    }
+
+    // Halo-exchange signal: every unit counts itself done after its stores (local and peer) are visible system-wide;
+    // the last one resets the counter and publishes the epoch to both neighbours, whose streams wait on that word
+    // (cuStreamWaitValue32) before they launch the next block.  No kernel ever spins on it.
+    if (A.done_counter != nullptr) {
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(A.done_counter, 1u);
+            if (prev == (unsigned)(A.total_units - 1)) {
+                *A.done_counter = 0u;
+                __threadfence_system();
+                if (A.flag_up) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.flag_up), "r"(A.epoch) : "memory");
+                if (A.flag_dn) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.flag_dn), "r"(A.epoch) : "memory");
+            }
+        }
     }
 }
 

@@ -14,6 +14,8 @@
 #include <cstring>
 #include <new>
 
+#include <unistd.h>
+
 #include "../../include/hsflow.h"
 #include "hs_common.cuh"
 #include "hs_launch.h"
@@ -39,6 +41,22 @@ static int fail(int code, const char* fmt, ...) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+// What one strip publishes to its neighbours (hsflow_strip_export): geometry for validation, CUDA IPC handles of the
+// two u/v ping-pong buffers and of the signal words, and -- for neighbours living in the same process -- the raw
+// pointers.  Must fit hsflow_strip_handle_t (include/hsflow.h).
+struct StripBlob {
+    uint32_t magic;
+    int32_t W, H, device;
+    int64_t pitch;
+    int64_t pid;
+    void* raw[3];                 // uvA, uvB, sig
+    cudaIpcMemHandle_t mem[3];
+};
+static_assert(sizeof(StripBlob) <= sizeof(hsflow_strip_handle_t), "strip handle blob too large");
+constexpr uint32_t kStripMagic = 0x48534631u;   // "HSF1"
 
 struct hsflow {
     int device = 0;
@@ -75,9 +93,30 @@ struct hsflow {
     cudaEvent_t ev0[4] = {}, ev1[4] = {};
     int ev_set[4] = {};
     long long launches = 0;
+    // peer transport of the row-strip mode: [0] = upper neighbour, [1] = lower neighbour
+    StreamWaitValue32Fn wait_value = nullptr;
+    unsigned* sig = nullptr;                       // device words: [0] epoch from the upper neighbour, [1] from the lower, [2] done counter
+    void* peer[2][3] = {};                         // neighbour's uvA, uvB, sig as seen from this device
+    int peer_ipc[2] = {};                          // mapped with cudaIpcOpenMemHandle (else same-process raw pointers)
+    int has_peer[2] = {};
+    int push_lo[2] = {}, push_hi[2] = {}, push_delta[2] = {};
+    int connected = 0;
+    unsigned epoch = 0;
 };
 
+static void strip_disconnect(hsflow* h) {
+    for (int d = 0; d < 2; ++d) {
+        if (h->has_peer[d] && h->peer_ipc[d])
+            for (int k = 0; k < 3; ++k) if (h->peer[d][k]) cudaIpcCloseMemHandle(h->peer[d][k]);
+        for (int k = 0; k < 3; ++k) h->peer[d][k] = nullptr;
+        h->has_peer[d] = h->peer_ipc[d] = 0;
+    }
+    h->connected = 0;
+    cudaGetLastError();
+}
+
 static void free_planes(hsflow* h) {
+    if (h->connected) strip_disconnect(h);         // the neighbours' mappings of OUR buffers die with the buffers: reconnect
     cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2);
     cudaFree(h->uA); cudaFree(h->uB); cudaFree(h->c0); cudaFree(h->dtmp);   // vA, vB, c1, c2 point into these
     h->f1 = h->f2 = h->fb1 = h->fb2 = nullptr;
@@ -93,7 +132,7 @@ static int effective_T(const hsflow* h) {
 }
 static bool use_stream_kernel(const hsflow* h, int t) {
     if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1) return false;
-    return t >= 2 || h->kernel_sel == 2;
+    return t >= 2 || h->kernel_sel == 2 || h->connected;   // the peer transport lives in the streaming kernel
 }
 
 // 4-D map {W, planes, H, pairs} over a row-interleaved buffer; box = 128 columns x all planes x RG rows
@@ -149,6 +188,10 @@ int hsflow_create(int device, hsflow_t** out) {
         return fail(HSFLOW_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
     }
     h->encode = (EncodeTiledFn)fn;
+    fn = nullptr;
+    e = cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) h->wait_value = (StreamWaitValue32Fn)fn;
+    else cudaGetLastError();
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(HSFLOW_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     h->stream = h->own_stream;
@@ -165,6 +208,7 @@ int hsflow_destroy(hsflow_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_planes(h);
+    cudaFree(h->sig);
     cudaFree(h->d_mask); cudaFree(h->d_count);
     for (int i = 0; i < 4; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -235,7 +279,11 @@ int hsflow_configure(hsflow_t* h, int W, int H, int P) {
     if (W <= 0 || H <= 0 || P <= 0) return fail(HSFLOW_EINVAL, "width, height, pairs must be positive");
     if (W > (1 << 24) || H > (1 << 24)) return fail(HSFLOW_EINVAL, "frame too large");
     CK(cudaSetDevice(h->device));
-    if (h->W == W && h->H == H && h->P == P && h->uA) { h->prepared = 0; h->top_edge = h->bottom_edge = 1; return HSFLOW_OK; }
+    if (h->W == W && h->H == H && h->P == P && h->uA) {
+        h->prepared = 0;
+        if (!h->connected) h->top_edge = h->bottom_edge = 1;   // a connected strip keeps its seams
+        return HSFLOW_OK;
+    }
     CK(cudaStreamSynchronize(h->stream));
     free_planes(h);
     h->W = W; h->H = H; h->P = P;
@@ -409,6 +457,17 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         A.z_c0 = 0;
         const int wpc = h->wpc > 0 ? std::min(h->wpc, 4) : 1;
         A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, nsx, n, t, wpc);
+        if (h->connected) {                        // fused halo exchange: seam rows go straight into the neighbours' buffers
+            const int dst = src == 0 ? 1 : 0;      // 0 = A planes, 1 = B planes; every strip flips in step
+            A.peer_up = h->has_peer[0] ? (float*)h->peer[0][dst] : nullptr;
+            A.peer_dn = h->has_peer[1] ? (float*)h->peer[1][dst] : nullptr;
+            A.up_lo = h->push_lo[0]; A.up_hi = h->push_hi[0]; A.up_delta = h->push_delta[0];
+            A.dn_lo = h->push_lo[1]; A.dn_hi = h->push_hi[1]; A.dn_delta = h->push_delta[1];
+            A.done_counter = h->sig + 2;
+            A.flag_up = h->has_peer[0] ? (unsigned*)h->peer[0][2] + 1 : nullptr;   // we are its lower neighbour
+            A.flag_dn = h->has_peer[1] ? (unsigned*)h->peer[1][2] + 0 : nullptr;   // we are its upper neighbour
+            A.epoch = h->epoch;
+        }
         CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uvA : h->tm_uvB, h->tm_c, A, n, wpc, h->stream));
         h->launches++;
         return HSFLOW_OK;
@@ -457,6 +516,32 @@ int hsflow_iterate(hsflow_t* h, int n) {
     CK(cudaSetDevice(h->device));
     const int T = effective_T(h);
     phase_begin(h, HSFLOW_PHASE_ITER);
+    if (h->connected) {
+        // Peer transport: every launch refreshes the neighbours' ghost rows itself, so the valid range never shrinks
+        // beyond one block.  After each launch the stream waits (cuStreamWaitValue32, no host involvement, no
+        // spinning kernel) until both neighbours published the same epoch: their seam rows are in our buffer and
+        // they finished reading the buffer our next launch stores into.
+        if (!use_stream_kernel(h, 1)) return fail(HSFLOW_EINVAL, "peer transport needs the streaming kernel (FAST math, update_v = 1)");
+        while (n > 0) {
+            const int t = std::min(n, T);
+            const int lo = h->top_edge ? 0 : t, hi = h->bottom_edge ? h->H : h->H - t;
+            if ((h->has_peer[0] && h->push_lo[0] < t) || (h->has_peer[1] && h->H - h->push_hi[1] < t) || lo >= hi)
+                return fail(HSFLOW_EINVAL, "strip has fewer ghost rows than the temporal block (%d)", t);
+            ++h->epoch;
+            int rc = run_block(h, t, h->cur, 0, h->P, lo, hi);
+            if (rc) return rc;
+            h->cur ^= 1;
+            for (int d = 0; d < 2; ++d)
+                if (h->has_peer[d]) {
+                    CUresult r = h->wait_value((CUstream)h->stream, (CUdeviceptr)(h->sig + d), h->epoch, CU_STREAM_WAIT_VALUE_GEQ);
+                    if (r != CUDA_SUCCESS) return fail(HSFLOW_ECUDA, "cuStreamWaitValue32 failed with CUresult %d", (int)r);
+                }
+            n -= t;
+        }
+        h->valid_lo = 0; h->valid_hi = h->H;
+        phase_end(h, HSFLOW_PHASE_ITER);
+        return HSFLOW_OK;
+    }
     while (n > 0) {
         const int t = std::min(n, T);
         const int lo = h->top_edge ? 0 : h->valid_lo + t;
@@ -532,6 +617,89 @@ int hsflow_compute(hsflow_t* h) {
     phase_end(h, HSFLOW_PHASE_ITER);
     h->cur = 0;
     h->prepared = 0;
+    return HSFLOW_OK;
+}
+
+int hsflow_strip_export(hsflow_t* h, hsflow_strip_handle_t* out) {
+    NEED(h);
+    if (!out) return fail(HSFLOW_EINVAL, "out is null");
+    if (!h->uA || h->P != 1) return fail(HSFLOW_EINVAL, "hsflow_strip_export needs a configured handle with one pair");
+    CK(cudaSetDevice(h->device));
+    if (!h->sig) {
+        if (cudaMalloc(&h->sig, 256) != cudaSuccess) { cudaGetLastError(); return fail(HSFLOW_ENOMEM, "cudaMalloc"); }
+    }
+    CK(cudaMemsetAsync(h->sig, 0, 256, h->stream));
+    CK(cudaStreamSynchronize(h->stream));          // the words are zero before any neighbour can see them
+    h->epoch = 0;
+    StripBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = kStripMagic; b.W = h->W; b.H = h->H; b.device = h->device; b.pitch = h->pitch; b.pid = (int64_t)getpid();
+    b.raw[0] = h->uA; b.raw[1] = h->uB; b.raw[2] = h->sig;
+    CK(cudaIpcGetMemHandle(&b.mem[0], h->uA));
+    CK(cudaIpcGetMemHandle(&b.mem[1], h->uB));
+    CK(cudaIpcGetMemHandle(&b.mem[2], h->sig));
+    memset(out, 0, sizeof *out);
+    memcpy(out, &b, sizeof b);
+    return HSFLOW_OK;
+}
+
+int hsflow_strip_connect(hsflow_t* h, const hsflow_strip_handle_t* up, int up_lo, int up_hi, int up_delta,
+                         const hsflow_strip_handle_t* down, int dn_lo, int dn_hi, int dn_delta) {
+    NEED(h);
+    if (!h->uA || h->P != 1 || !h->sig) return fail(HSFLOW_EINVAL, "hsflow_strip_export first");
+    if (!h->wait_value) return fail(HSFLOW_ECUDA, "cuStreamWaitValue32 not available from the driver");
+    CK(cudaSetDevice(h->device));
+    if (h->connected) strip_disconnect(h);
+    const hsflow_strip_handle_t* blobs[2] = {up, down};
+    const int lo[2] = {up_lo, dn_lo}, hi[2] = {up_hi, dn_hi}, delta[2] = {up_delta, dn_delta};
+    for (int d = 0; d < 2; ++d) {
+        if (!blobs[d]) continue;
+        StripBlob b;
+        memcpy(&b, blobs[d], sizeof b);
+        if (b.magic != kStripMagic) { strip_disconnect(h); return fail(HSFLOW_EINVAL, "not a strip handle"); }
+        if (b.W != h->W || b.pitch != h->pitch) { strip_disconnect(h); return fail(HSFLOW_EINVAL, "neighbour strip has a different width (%d vs %d)", b.W, h->W); }
+        if (lo[d] < 0 || hi[d] < lo[d] || hi[d] > h->H || lo[d] + delta[d] < 0 || hi[d] + delta[d] > b.H) {
+            strip_disconnect(h);
+            return fail(HSFLOW_EINVAL, "seam rows [%d,%d) + %d fall outside the strips (%d and %d rows)", lo[d], hi[d], delta[d], h->H, b.H);
+        }
+        if (b.pid == (int64_t)getpid()) {          // same process: plain peer access
+            if (b.device != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    strip_disconnect(h);
+                    return fail(HSFLOW_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", b.device, cudaGetErrorString(e));
+                }
+                cudaGetLastError();
+            }
+            for (int k = 0; k < 3; ++k) h->peer[d][k] = b.raw[k];
+            h->peer_ipc[d] = 0;
+        } else {
+            h->peer_ipc[d] = 1;
+            h->has_peer[d] = 1;                    // so that a partial failure closes what was opened
+            for (int k = 0; k < 3; ++k) {
+                cudaError_t e = cudaIpcOpenMemHandle(&h->peer[d][k], b.mem[k], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    h->peer[d][k] = nullptr;
+                    strip_disconnect(h);
+                    return fail(HSFLOW_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+                }
+            }
+        }
+        h->has_peer[d] = 1;
+        h->push_lo[d] = lo[d]; h->push_hi[d] = hi[d]; h->push_delta[d] = delta[d];
+    }
+    h->top_edge = h->has_peer[0] ? 0 : 1;
+    h->bottom_edge = h->has_peer[1] ? 0 : 1;
+    h->connected = 1;
+    h->prepared = 0;
+    return HSFLOW_OK;
+}
+
+int hsflow_strip_disconnect(hsflow_t* h) {
+    NEED(h);
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    strip_disconnect(h);
     return HSFLOW_OK;
 }
 

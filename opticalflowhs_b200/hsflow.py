@@ -57,6 +57,9 @@ SIGNATURES = {
     "hsflow_iterate": (C.c_int, [_P, C.c_int]),
     "hsflow_halo_refreshed": (C.c_int, [_P]),
     "hsflow_sync": (C.c_int, [_P]),
+    "hsflow_strip_export": (C.c_int, [_P, _P]),
+    "hsflow_strip_connect": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int]),
+    "hsflow_strip_disconnect": (C.c_int, [_P]),
     "hsflow_read_uv": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
     "hsflow_read_derivatives": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t]),
     "hsflow_write_uv": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
@@ -203,6 +206,25 @@ class HSFlow:
 
     def sync(self):
         self._ck(self._L.hsflow_sync(self._h)); return self
+
+    # ---- row strips with peer transport (seam rows stored into the neighbours' buffers by the iteration kernel)
+    STRIP_HANDLE_BYTES = 320
+
+    def strip_export(self):
+        buf = C.create_string_buffer(self.STRIP_HANDLE_BYTES)
+        self._ck(self._L.hsflow_strip_export(self._h, buf))
+        return buf.raw
+
+    def strip_connect(self, up=None, up_rows=(0, 0, 0), down=None, down_rows=(0, 0, 0)):
+        """up/down: handle bytes of the neighbours (None at a true image edge); *_rows = (lo, hi, delta): output rows
+        [lo, hi) of this strip are also stored at row + delta of that neighbour's buffer."""
+        ub = C.create_string_buffer(up, self.STRIP_HANDLE_BYTES) if up is not None else None
+        db = C.create_string_buffer(down, self.STRIP_HANDLE_BYTES) if down is not None else None
+        self._ck(self._L.hsflow_strip_connect(self._h, ub, *[int(x) for x in up_rows], db, *[int(x) for x in down_rows]))
+        return self
+
+    def strip_disconnect(self):
+        self._ck(self._L.hsflow_strip_disconnect(self._h)); return self
 
     # ---- results
     def read_uv(self, pair=0):

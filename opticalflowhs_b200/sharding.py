@@ -6,11 +6,16 @@ One process per GPU (torchrun), `torch.distributed` only for plumbing:
                       data-path collective (`pair_block`);
   * row strips     -- one very large frame cut into `world` horizontal strips.  Every rank keeps
                       `ghost` extra rows of u, v (and of the frames / coefficients) on each inner
-                      seam, advances `ghost` Jacobi iterations per exchange with the temporally
-                      blocked kernel and then swaps seam rows with its two neighbours
-                      (`StripSolver.exchange`: NCCL send/recv over NVLink, non-periodic).  The
-                      result is bit-identical to the single-GPU run because every pixel sees the
-                      same operation sequence.
+                      seam.  Two transports for the seam rows:
+                        "p2p"  (default on GPUs) the iteration kernel itself stores the rows its
+                               neighbours keep as ghosts into THEIR buffers over NVLink peer memory
+                               and publishes an epoch word; streams wait on the word between
+                               launches (hsflow_strip_connect).  No exchange step, no collective:
+                               torch.distributed only carries the IPC handles once.
+                        "nccl" advance `ghost` iterations, then swap seam rows with both
+                               neighbours (`StripSolver.exchange`: NCCL send/recv, non-periodic).
+                      Either way the result is bit-identical to the single-GPU run because every
+                      pixel sees the same operation sequence.
 
 The solver talks to an engine object with the HSFlow method set (configure, set_strip,
 set_frames / synth_frames, prepare, iterate, halo_refreshed) plus a callable returning the flow
@@ -62,6 +67,23 @@ class StripPlan:
     def bottom_ghost(self):
         return self.b - self.hi
 
+    def neighbour(self, rank):
+        return StripPlan(self.height, self.world, rank, self.ghost)
+
+    def push_rows(self, direction):
+        """Peer transport: (lo, hi, delta) in THIS rank's buffer rows -- output rows [lo, hi) are also stored at
+        row + delta of the neighbour's buffer (direction -1: upper neighbour, whose bottom ghost rows they are;
+        +1: lower neighbour, its top ghost rows).  None at a true image edge."""
+        if direction < 0:
+            if self.is_top:
+                return None
+            n = self.neighbour(self.rank - 1)
+            return self.lo - self.a, n.b - self.a, self.a - n.a
+        if self.is_bottom:
+            return None
+        n = self.neighbour(self.rank + 1)
+        return n.a - self.a, self.hi - self.a, self.a - n.a
+
     def halo_bytes_per_exchange(self, width):
         """fp32 bytes this rank SENDS per exchange (u and v)."""
         rows = (0 if self.is_top else self.ghost + 1) + (0 if self.is_bottom else self.ghost)
@@ -88,16 +110,43 @@ def engine_uv_tensors(engine, device_index):
 
 
 class StripSolver:
-    """Row-strip Horn-Schunck over `world` ranks with per-temporal-block halo exchange."""
+    """Row-strip Horn-Schunck over `world` ranks.  transport "p2p": seam rows pushed by the iteration kernel
+    into the neighbours' buffers (needs ghost >= temporal block; one exchange per launch, fused); "nccl": halo
+    exchange every `ghost` iterations with send/recv."""
 
-    def __init__(self, engine, width, height, rank, world, ghost, dist=None, uv_tensors=None):
+    def __init__(self, engine, width, height, rank, world, ghost, dist=None, uv_tensors=None, transport="nccl"):
+        if transport not in ("nccl", "p2p"):
+            raise ValueError("transport must be 'nccl' or 'p2p'")
         self.e, self.W, self.H = engine, width, height
         self.plan = StripPlan(height, world, rank, ghost)
         self.dist = dist
+        self.transport = transport if world > 1 else "nccl"
         self._uv = uv_tensors or (lambda: engine_uv_tensors(engine, engine.device))
         self.exchanges = 0
         engine.configure(width, self.plan.rows, 1)
         engine.set_strip(self.plan.is_top, self.plan.is_bottom)
+        if self.transport == "p2p":
+            self._connect()
+
+    def _connect(self):
+        """Carry every strip's handle to its neighbours (one object all-gather, plumbing only) and connect."""
+        p, dist = self.plan, self.dist
+        mine = self.e.strip_export()
+        handles = [None] * p.world
+        dist.all_gather_object(handles, mine)
+        up, dn = p.push_rows(-1), p.push_rows(+1)
+        self.e.strip_connect(handles[p.rank - 1] if up else None, up or (0, 0, 0),
+                             handles[p.rank + 1] if dn else None, dn or (0, 0, 0))
+        dist.barrier()                 # every strip is connected before anyone launches
+
+    def close(self):
+        """Peer mappings must go before any strip frees its buffers."""
+        if self.transport == "p2p":
+            self.e.sync()
+            self.dist.barrier()
+            self.e.strip_disconnect()
+            self.dist.barrier()
+            self.transport = "nccl"
 
     # ---- frames -------------------------------------------------------------------------------
     def load_synth(self, seed):
@@ -130,6 +179,11 @@ class StripSolver:
     # ---- driver ---------------------------------------------------------------------------------
     def run(self, iterations):
         self.e.prepare()
+        if self.transport == "p2p":    # the engine exchanges inside every launch
+            self.e.iterate(iterations)
+            T = max(1, self.e.temporal_block)
+            self.exchanges += -(-iterations // T)
+            return self
         done = 0
         while done < iterations:
             step = min(self.plan.ghost, iterations - done)

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, W, H, N, T, ghost, out_dir):
+def _worker(rank, world, port, W, H, N, T, ghost, out_dir, transport="nccl"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -34,12 +34,15 @@ def _worker(rank, world, port, W, H, N, T, ghost, out_dir):
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     eng = P.HSFlow(rank)
     eng.set_stream(stream.cuda_stream).set_params(15.0, N, P.STENCIL_CL8, True, T)
-    s = StripSolver(eng, W, H, rank, world, ghost, dist=dist)
+    s = StripSolver(eng, W, H, rank, world, ghost, dist=dist, transport=transport)
     s.load_synth(4321)
     s.run(N)
+    if transport == "p2p":
+        s.run(N)                  # second run on the same connection (epochs keep counting, ghost rows are re-zeroed)
     u, v = eng.read_uv()
     np.save(os.path.join(out_dir, f"u{rank}.npy"), s.owned_rows(u))
     np.save(os.path.join(out_dir, f"v{rank}.npy"), s.owned_rows(v))
+    s.close()
     dist.barrier(); dist.destroy_process_group(); eng.close()
 
 
@@ -56,6 +59,26 @@ def test_row_strips_over_nccl_bit_identical_to_one_gpu(tmp_path, T, ghost, N):
         e.configure(W, H, 1).synth_frames(0, 0, 4321).compute()
         whole = e.read_uv()
     mp.spawn(_worker, args=(world, _free_port(), W, H, N, T, ghost, str(tmp_path)), nprocs=world, join=True)
+    u = np.concatenate([np.load(tmp_path / f"u{r}.npy") for r in range(world)])
+    v = np.concatenate([np.load(tmp_path / f"v{r}.npy") for r in range(world)])
+    assert (u.view(np.uint32) == whole[0].view(np.uint32)).all() and (v.view(np.uint32) == whole[1].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("T,ghost,N", [(4, 4, 22), (4, 6, 40), (1, 1, 7), (8, 8, 19)])
+def test_row_strips_with_peer_stores_bit_identical_to_one_gpu(tmp_path, T, ghost, N):
+    """transport="p2p": the iteration kernel pushes the seam rows into the neighbours' buffers over NVLink and
+    signals an epoch word; no exchange step.  Must equal the single-GPU field bit for bit."""
+    world = min(_ngpu(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    import opticalflowhs_b200 as P
+    W, H = 1000, 64 * world + 9
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, T)
+        e.configure(W, H, 1).synth_frames(0, 0, 4321).compute()
+        whole = e.read_uv()
+    mp.spawn(_worker, args=(world, _free_port(), W, H, N, T, ghost, str(tmp_path), "p2p"), nprocs=world, join=True)
     u = np.concatenate([np.load(tmp_path / f"u{r}.npy") for r in range(world)])
     v = np.concatenate([np.load(tmp_path / f"v{r}.npy") for r in range(world)])
     assert (u.view(np.uint32) == whole[0].view(np.uint32)).all() and (v.view(np.uint32) == whole[1].view(np.uint32)).all()
