@@ -48,6 +48,58 @@ __device__ __forceinline__ void normalise_coefs(float ex, float ey, float et, fl
     c = __fmul_rn(et, r);
 }
 
+// ---- packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2: fma.rn.f32x2 etc., sm_100+) --------------------
+// One instruction works on TWO adjacent pixels held in an aligned register pair.  Each half is the
+// IEEE round-to-nearest result of the scalar operation, so the packed FAST formulation is bit-identical
+// to the scalar one above (k_jacobi1) while issuing half the arithmetic instructions: the streaming
+// kernel is bound by instruction issue, not by the FMA pipe (tools/microbench/ffma2_bench.cu: FFMA2
+// has the flop rate of FFMA at half the issue slots).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// h = W + E for the four pixels of a lane (l, r: the neighbouring lanes' edge pixels), as two packed pairs
+__device__ __forceinline__ void hsum4(const float (&c)[4], float l, float r, f32x2 (&h)[2]) {
+    h[0] = pk2(__fadd_rn(l, c[1]), __fadd_rn(c[0], c[2]));
+    h[1] = pk2(__fadd_rn(c[1], c[3]), __fadd_rn(c[2], r));
+}
+template <int ST> __device__ __forceinline__ f32x2 rowG2(f32x2 c, f32x2 h) {
+    return ST == ST_CL8 ? fma2(pk2(2.0f, 2.0f), c, h) : c;
+}
+template <int ST> __device__ __forceinline__ f32x2 pOf2(f32x2 gprev, f32x2 h) {
+    return ST == ST_CL8 ? fma2(pk2(2.0f, 2.0f), h, gprev) : add2(gprev, h);
+}
+template <int ST> __device__ __forceinline__ f32x2 combine2(f32x2 p, f32x2 G) {
+    const float k = ST == ST_CL8 ? (float)(1.0 / 12) : 0.25f;
+    return mul2(pk2(k, k), add2(p, G));
+}
+// t = a*ub + (b*vb + c); u = ub - a t; v = vb - b t for two pixels (na, nb = -a, -b: the negation folds into FFMA2)
+__device__ __forceinline__ void update_fast2(f32x2 ub, f32x2 vb, f32x2 a, f32x2 b, f32x2 c, f32x2 na, f32x2 nb, f32x2& un, f32x2& vn) {
+    const f32x2 t = fma2(a, ub, fma2(b, vb, c));
+    un = fma2(na, t, ub);
+    vn = fma2(nb, t, vb);
+}
+
 // ---- EXACT formulation: Kernels.cl:55-58 and 84-86, one rounding per operator -------------
 __device__ __forceinline__ float avg_exact(float we, float wd, float W, float E, float N, float S,
                                            float NW, float NE, float SW, float SE) {

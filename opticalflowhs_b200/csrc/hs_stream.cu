@@ -168,12 +168,13 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     }
     __syncwarp();
 
-    // register pipeline: per stage, field (u: 0..3, v: 4..7) and pixel two partial sums
-    float p[T][8], g[T][8];
+    // register pipeline: per stage and field two partial sums per pixel, held as packed pixel pairs
+    // (index 0: u of pixels 0,1; 1: u of pixels 2,3; 2, 3: v likewise) for FFMA2 / FADD2 / FMUL2
+    f32x2 p[T][4], g[T][4];
 #pragma unroll
     for (int s = 0; s < T; ++s)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { p[s][j] = 0.f; g[s][j] = 0.f; }
+        for (int j = 0; j < 4; ++j) { p[s][j] = 0ull; g[s][j] = 0ull; }
 
     const bool lane_out = (lane >= C::HL / 4) && (lane < 32 - C::HL / 4) && (col0 < W);
     float* uo = A.u_out + (size_t)z * A.out_pair_pitch + col0;
@@ -199,6 +200,16 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         }
     };
 
+    // time step S+1 of one row from its averages and coefficients (two packed pixel pairs per field)
+    auto update_rows = [&](const f32x2 (&ub)[2], const f32x2 (&vb)[2], const float4& ka, const float4& kb, const float4& kc,
+                           float (&cu)[4], float (&cv)[4]) {
+        f32x2 un, vn;
+        update_fast2(ub[0], vb[0], pk2(ka.x, ka.y), pk2(kb.x, kb.y), pk2(kc.x, kc.y), pk2(-ka.x, -ka.y), pk2(-kb.x, -kb.y), un, vn);
+        unpk2(un, cu[0], cu[1]); unpk2(vn, cv[0], cv[1]);
+        update_fast2(ub[1], vb[1], pk2(ka.z, ka.w), pk2(kb.z, kb.w), pk2(kc.z, kc.w), pk2(-ka.z, -ka.w), pk2(-kb.z, -kb.w), un, vn);
+        unpk2(un, cu[2], cu[3]); unpk2(vn, cv[2], cv[3]);
+    };
+
     // one stage-row in steady state: time step S of one row (cu, cv) -> time step S+1 of the row
     // above it, written back into cu, cv.  coff = byte offset of that row's coefficients.
     auto stage_row = [&](auto edge_tag, auto s_tag, float (&cu)[4], float (&cv)[4], const int coff) {
@@ -211,21 +222,19 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         const float4 ka = *reinterpret_cast<const float4*>(sa_l + coff);
         const float4 kb = *reinterpret_cast<const float4*>(sa_l + ROWB + coff);
         const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * ROWB + coff);
-        const float hu[4] = {__fadd_rn(lu, cu[1]), __fadd_rn(cu[0], cu[2]), __fadd_rn(cu[1], cu[3]), __fadd_rn(cu[2], ru)};
-        const float hv[4] = {__fadd_rn(lv, cv[1]), __fadd_rn(cv[0], cv[2]), __fadd_rn(cv[1], cv[3]), __fadd_rn(cv[2], rv)};
-        float ub[4], vb[4];
+        f32x2 hu[2], hv[2], ub[2], vb[2];
+        hsum4(cu, lu, ru, hu);
+        hsum4(cv, lv, rv, hv);
+        const f32x2 c2u[2] = {pk2(cu[0], cu[1]), pk2(cu[2], cu[3])}, c2v[2] = {pk2(cv[0], cv[1]), pk2(cv[2], cv[3])};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float Gu = rowG<ST>(cu[j], hu[j]), Gv = rowG<ST>(cv[j], hv[j]);
-            ub[j] = combine<ST>(p[S][j], Gu);
-            vb[j] = combine<ST>(p[S][4 + j], Gv);
-            p[S][j] = pOf<ST>(g[S][j], hu[j]); g[S][j] = Gu;
-            p[S][4 + j] = pOf<ST>(g[S][4 + j], hv[j]); g[S][4 + j] = Gv;
+        for (int j = 0; j < 2; ++j) {
+            const f32x2 Gu = rowG2<ST>(c2u[j], hu[j]), Gv = rowG2<ST>(c2v[j], hv[j]);
+            ub[j] = combine2<ST>(p[S][j], Gu);
+            vb[j] = combine2<ST>(p[S][2 + j], Gv);
+            p[S][j] = pOf2<ST>(g[S][j], hu[j]); g[S][j] = Gu;
+            p[S][2 + j] = pOf2<ST>(g[S][2 + j], hv[j]); g[S][2 + j] = Gv;
         }
-        update_fast(ub[0], vb[0], ka.x, kb.x, kc.x, cu[0], cv[0]);
-        update_fast(ub[1], vb[1], ka.y, kb.y, kc.y, cu[1], cv[1]);
-        update_fast(ub[2], vb[2], ka.z, kb.z, kc.z, cu[2], cv[2]);
-        update_fast(ub[3], vb[3], ka.w, kb.w, kc.w, cu[3], cv[3]);
+        update_rows(ub, vb, ka, kb, kc, cu, cv);
     };
 
     // ---- generic tick: pipeline fill, bottom-edge drain, tiny frames (runtime predicates) ----------
@@ -253,37 +262,39 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             if (rho < rs || rho > H) have = false;
             else if (rho == H) { virt = true; have = true; }   // row H == row H-1 (clamp)
             if (!have) continue;
-            float ub[4], vb[4];
+            f32x2 ub[2], vb[2];
             if (virt) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ub[j] = combine<ST>(p[S][j], g[S][j]);
-                    vb[j] = combine<ST>(p[S][4 + j], g[S][4 + j]);
+                for (int j = 0; j < 2; ++j) {
+                    ub[j] = combine2<ST>(p[S][j], g[S][j]);
+                    vb[j] = combine2<ST>(p[S][2 + j], g[S][2 + j]);
                 }
             } else {
                 if (edge && wmis) { sanitize_right(cu, col0, W); sanitize_right(cv, col0, W); }
                 float lu = __shfl_up_sync(kFull, cu[3], 1), ru = __shfl_down_sync(kFull, cu[0], 1);
                 float lv = __shfl_up_sync(kFull, cv[3], 1), rv = __shfl_down_sync(kFull, cv[0], 1);
                 if (edge) { clamp_lr(cu, col0, W, lu, ru); clamp_lr(cv, col0, W, lv, rv); }
-                const float hu[4] = {__fadd_rn(lu, cu[1]), __fadd_rn(cu[0], cu[2]), __fadd_rn(cu[1], cu[3]), __fadd_rn(cu[2], ru)};
-                const float hv[4] = {__fadd_rn(lv, cv[1]), __fadd_rn(cv[0], cv[2]), __fadd_rn(cv[1], cv[3]), __fadd_rn(cv[2], rv)};
+                f32x2 hu[2], hv[2];
+                hsum4(cu, lu, ru, hu);
+                hsum4(cv, lv, rv, hv);
+                const f32x2 c2u[2] = {pk2(cu[0], cu[1]), pk2(cu[2], cu[3])}, c2v[2] = {pk2(cv[0], cv[1]), pk2(cv[2], cv[3])};
                 if (rho == rs) {                   // first row of this stage: replicate upwards
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float Gu = rowG<ST>(cu[j], hu[j]), Gv = rowG<ST>(cv[j], hv[j]);
-                        p[S][j] = pOf<ST>(Gu, hu[j]); g[S][j] = Gu;
-                        p[S][4 + j] = pOf<ST>(Gv, hv[j]); g[S][4 + j] = Gv;
+                    for (int j = 0; j < 2; ++j) {
+                        const f32x2 Gu = rowG2<ST>(c2u[j], hu[j]), Gv = rowG2<ST>(c2v[j], hv[j]);
+                        p[S][j] = pOf2<ST>(Gu, hu[j]); g[S][j] = Gu;
+                        p[S][2 + j] = pOf2<ST>(Gv, hv[j]); g[S][2 + j] = Gv;
                     }
                     have = false;
                     continue;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float Gu = rowG<ST>(cu[j], hu[j]), Gv = rowG<ST>(cv[j], hv[j]);
-                    ub[j] = combine<ST>(p[S][j], Gu);
-                    vb[j] = combine<ST>(p[S][4 + j], Gv);
-                    p[S][j] = pOf<ST>(g[S][j], hu[j]); g[S][j] = Gu;
-                    p[S][4 + j] = pOf<ST>(g[S][4 + j], hv[j]); g[S][4 + j] = Gv;
+                for (int j = 0; j < 2; ++j) {
+                    const f32x2 Gu = rowG2<ST>(c2u[j], hu[j]), Gv = rowG2<ST>(c2v[j], hv[j]);
+                    ub[j] = combine2<ST>(p[S][j], Gu);
+                    vb[j] = combine2<ST>(p[S][2 + j], Gv);
+                    p[S][j] = pOf2<ST>(g[S][j], hu[j]); g[S][j] = Gu;
+                    p[S][2 + j] = pOf2<ST>(g[S][2 + j], hv[j]); g[S][2 + j] = Gv;
                 }
             }
             // time step S+1 of row rho-1 (coefficients of that row)
@@ -291,10 +302,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             const float4 ka = *reinterpret_cast<const float4*>(sa_l + q);
             const float4 kb = *reinterpret_cast<const float4*>(sa_l + ROWB + q);
             const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * ROWB + q);
-            update_fast(ub[0], vb[0], ka.x, kb.x, kc.x, cu[0], cv[0]);
-            update_fast(ub[1], vb[1], ka.y, kb.y, kc.y, cu[1], cv[1]);
-            update_fast(ub[2], vb[2], ka.z, kb.z, kc.z, cu[2], cv[2]);
-            update_fast(ub[3], vb[3], ka.w, kb.w, kc.w, cu[3], cv[3]);
+            update_rows(ub, vb, ka, kb, kc, cu, cv);
         }
         const int ro = r - T;
         if (have && lane_out && ro >= R0 && ro < R1) {
