@@ -12,8 +12,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhsflow.so")
-SOURCES = ["hs_kernels.cu", "hs_stream.cu", "hsflow_capi.cu"]
-HEADERS = ["hs_common.cuh", "hs_launch.h", os.path.join("..", "..", "include", "hsflow.h")]
+STREAM_DEPTHS = range(1, 9)             # hs_stream_inst.cu is compiled once per temporal-block depth T
+SOURCES = ["hs_kernels.cu", "hs_stream.cu", "hsflow_capi.cu", "hs_stream_inst.cu"]
+HEADERS = ["hs_common.cuh", "hs_launch.h", "hs_stream.cuh", os.path.join("..", "..", "include", "hsflow.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -41,10 +42,12 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    jobs = [(src, [], src.replace(".cu", ".o")) for src in SOURCES if src != "hs_stream_inst.cu"]
+    jobs += [("hs_stream_inst.cu", [f"-DHS_STREAM_T={t}"], f"hs_stream_t{t}.o") for t in STREAM_DEPTHS]
+    for src, defs, objname in jobs:
+        obj = os.path.join(HERE, "build", objname)
+        cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src + " " + " ".join(defs), subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
