@@ -36,17 +36,25 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, extra=()):
+    """variant/extra: A/B kernel experiments -- libhsflow_<variant>.so built with additional nvcc flags
+    (select it at run time with HSFLOW_LIBRARY=...); the product is the plain libhsflow.so."""
+    if variant:
+        return _build(os.path.join(HERE, f"libhsflow_{variant}.so"), os.path.join(HERE, "build", variant), list(extra), verbose)
     if not force and not needs_build():
         return LIB
+    return _build(LIB, os.path.join(HERE, "build"), [], verbose)
+
+
+def _build(lib, objdir, extra, verbose):
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     jobs = [(src, [], src.replace(".cu", ".o")) for src in SOURCES if src != "hs_stream_inst.cu"]
     jobs += [("hs_stream_inst.cu", [f"-DHS_STREAM_T={t}"], f"hs_stream_t{t}.o") for t in STREAM_DEPTHS]
     for src, defs, objname in jobs:
-        obj = os.path.join(HERE, "build", objname)
-        cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, objname)
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src + " " + " ".join(defs), subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
@@ -55,10 +63,14 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    cmd = [_nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m opticalflowhs_b200.build [--force] [-v] [--variant NAME -- extra nvcc flags ...]
+    args = sys.argv[1:]
+    extra = args[args.index("--") + 1:] if "--" in args else []
+    variant = args[args.index("--variant") + 1] if "--variant" in args else None
+    print(build(force="--force" in args, verbose="-v" in args, variant=variant, extra=extra))

@@ -65,6 +65,7 @@ struct StreamArgs {
 
 struct StreamGeom {             // filled by stream_geometry()
     int halo, valid_w, smem_per_warp, max_T;
+    int rows_per_box;           // rows of one TMA box (2, 3 or 4): selects the tensor maps the launch needs
 };
 
 cudaError_t launch_deriv(const DerivArgs& A, int fmt, int pairs, cudaStream_t s);
@@ -78,11 +79,11 @@ cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long l
 
 // temporally blocked streaming kernel (hs_stream.cu)
 constexpr int kMaxT = 8;
-constexpr int kStreamRowsPerBox = 2;   // TMA box = 128 columns x 2 rows
 StreamGeom stream_geometry(int T);
 cudaError_t stream_prepare(int device);     // opt in to large dynamic shared memory for every instantiation
 int stream_warps_per_sm(int T, int stencil, int warps_per_cta);   // resident warps per SM (occupancy API)
-// maps: row-interleaved u/v source {W,2,H,pairs} and coefficients {W,3,H,pairs}.  warps_per_cta in 1..4.
+// maps: row-interleaved u/v source {W,2,H,pairs} and coefficients {W,3,H,pairs}, box = 128 columns x all planes x
+// stream_geometry(T).rows_per_box rows.  warps_per_cta in 1..4.
 cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tm_uv, const CUtensorMap& tm_c,
                                  StreamArgs A, int pairs, int warps_per_cta, cudaStream_t s);
 

@@ -13,7 +13,7 @@ HS_DECL(1) HS_DECL(2) HS_DECL(3) HS_DECL(4) HS_DECL(5) HS_DECL(6) HS_DECL(7) HS_
 
 template <int T> static StreamGeom geom_of() {
     using C = typename DefaultCfg<T>::type;
-    return StreamGeom{C::HL, C::VALIDW, C::SMEM_WARP, kMaxT};
+    return StreamGeom{C::HL, C::VALIDW, C::SMEM_WARP, kMaxT, C::RG};
 }
 StreamGeom stream_geometry(int T) {
     switch (T) {

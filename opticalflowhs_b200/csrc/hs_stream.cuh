@@ -76,41 +76,53 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
         : "memory");
 }
 
+// 16 bytes of shared memory at `base + OFF` (OFF a compile-time constant: the address is "register + immediate").
+// Volatile on purpose: consecutive ticks read the same coefficient rows (stage S+1 of tick J+1 uses the row stage S of
+// tick J used); once every address of a trip is a constant expression the compiler would merge those loads and keep
+// 12 registers per row alive across whole ticks -- measured 17-34 % slower (spills, no ILP left) than re-reading.
+template <int OFF> __device__ __forceinline__ float4 lds128(uint32_t base) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base), "n"(OFF));
+    return v;
+}
+
 // ---- geometry ------------------------------------------------------------------------------------
-template <int T, int RG, int NGC, int NGUV> struct StreamCfg {
+template <int T, int RG_, int NGC_, int NGUV_> struct StreamCfg {
+    static constexpr int RG = RG_, NGC = NGC_, NGUV = NGUV_;
     static constexpr int HL = (T + 3) / 4 * 4;              // column halo per side, multiple of 4
     static constexpr int VALIDW = kStripW - 2 * HL;         // columns a strip produces
     static constexpr int NRC = NGC * RG;                    // coefficient ring rows
     static constexpr int NRUV = NGUV * RG;                  // u/v ring rows
     static constexpr int ROWB = kStripW * 4;                // bytes per ring row
     static constexpr int SMEM_WARP = (3 * NRC + 2 * NRUV) * ROWB + 128;   // coefficient ring + u/v ring + mbarriers
-    // a coefficient group is refilled at the end of the RG-tick body that retires it; it must
-    // have been issued at least one body before it is needed
-    static_assert((NGC - 1) * RG >= T + 2, "coefficient ring too short for the stage lag");
+    // A coefficient group is in use for DRET + 1 trips (one trip = RG ticks = one row group) and is refilled at the
+    // end of the trip that retires it; one more slot keeps a whole trip between the refill and its first use.
+    static constexpr int DRET = (T + RG - 1) / RG;
+    static_assert(NGC >= DRET + 2, "coefficient ring too short for the stage lag");
+    static_assert(NGUV == 2, "the steady-state loop toggles between two u/v slots");
     static_assert(NGC + NGUV <= 16, "barrier block is 128 bytes");
-    static_assert(RG == 2, "the steady-state body is written for 2-row TMA boxes");
 };
+// Rows per TMA box (= ticks per steady-state trip).  Taller boxes spread the per-trip overhead (barrier waits, TMA
+// issue, ring bookkeeping, the register moves ptxas leaves on the loop back edge) over more stage-rows, but the
+// coefficient ring needs (ceil(T/RG) + 2) x RG rows and the u/v ring 2 x RG rows per warp, eight warps have to fit
+// the 227 KB of an SM, and the unrolled trip has to stay inside the 32 KB instruction cache:
+//   T <= 3: 2 rows (occupancy of the shallow blocks)      T = 4: 4 rows (12 + 8 ring rows, 26 KB)
+//   T = 5, 6: 3 rows (12 + 6 ring rows, 24 KB)            T = 7, 8: 2 rows (12 + 4 ring rows, 22 KB)
+// HS_STREAM_RG="{2,2,2,2,4,3,3,2,2}" (index = T) overrides the table for experiments.
+#ifndef HS_STREAM_RG
+#define HS_STREAM_RG {2, 2, 2, 2, 4, 3, 3, 2, 2}
+#endif
+constexpr int stream_rows_per_box(int T) {
+    constexpr int tab[9] = HS_STREAM_RG;
+    return tab[T];
+}
 template <int T> struct DefaultCfg {
-    static constexpr int RG = kStreamRowsPerBox;
-    static constexpr int NGC = T <= 4 ? 4 : 6;              // 8 or 12 coefficient rows
-    static constexpr int NGUV = 2;                          // 4 u/v rows
-    // Main loop of interior strips unrolled over one whole coefficient-ring period (all shared-memory offsets become
-    // immediates: 56 instead of 84 instructions per stage-row at T = 4).  Measured SLOWER on B200 (T = 4: 731 k vs
-    // 774 k Mpixel-iterations/s sustained, T = 8: 566 k vs 773 k): the kernel is bound by dependency latency at two
-    // warps per scheduler, not by issue slots, and the 29-79 KB loop bodies fall out of the instruction caches.
-    static constexpr bool PERIOD_UNROLL = false;
+    static constexpr int RG = stream_rows_per_box(T);
+    static constexpr int NGC = (T + RG - 1) / RG + 2;
+    static constexpr int NGUV = 2;
     using type = StreamCfg<T, RG, NGC, NGUV>;
 };
-
-// ring index arithmetic: power-of-two rings wrap with one AND
-template <int SIZE_BYTES> __device__ __forceinline__ int wrap_down(int off) {   // off in (-SIZE, SIZE)
-    if ((SIZE_BYTES & (SIZE_BYTES - 1)) == 0) return off & (SIZE_BYTES - 1);
-    return off < 0 ? off + SIZE_BYTES : off;
-}
-template <int SIZE_BYTES> __device__ __forceinline__ int wrap_up(int off) {     // off in [0, 2*SIZE)
-    if ((SIZE_BYTES & (SIZE_BYTES - 1)) == 0) return off & (SIZE_BYTES - 1);
-    return off >= SIZE_BYTES ? off - SIZE_BYTES : off;
-}
 
 // ---- the kernel -----------------------------------------------------------------------------------
 #ifndef HS_STREAM_MIN_CTAS
@@ -120,7 +132,7 @@ template <int T, int ST, bool PEER>
 __global__ void __launch_bounds__(128, HS_STREAM_MIN_CTAS)
 k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant__ CUtensorMap tm_c, const StreamArgs A) {
     using C = typename DefaultCfg<T>::type;
-    constexpr int RG = DefaultCfg<T>::RG, NGC = DefaultCfg<T>::NGC, NGUV = DefaultCfg<T>::NGUV;
+    constexpr int RG = C::RG, NGC = C::NGC, NGUV = C::NGUV, DRET = C::DRET;
     constexpr int NRC = C::NRC, NRUV = C::NRUV, ROWB = C::ROWB;
     // rings are row-interleaved like the planes in HBM: a|b|c of one row are adjacent (CROW bytes), u|v likewise
     constexpr int CROW = 3 * ROWB, UROW = 2 * ROWB;
@@ -159,15 +171,17 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     const uint8_t* sa_l = wsm + lane * 16;                  // this lane's 16-byte column group
     const uint8_t* su_l = wsm + CB + lane * 16;
     const uint32_t sa32 = smem_u32(wsm), su32 = sa32 + CB;
-    const uint32_t bar0 = su32 + UB;                        // cbar[NGC] then uvbar[NGUV]
+    const uint32_t bar0 = su32 + UB;                        // uvbar[NGUV] then cbar[NGC], 8 bytes each
+    auto ubar_of = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
+    auto cbar_of = [&](int slot) { return bar0 + 8u * (uint32_t)(NGUV + slot); };
 
     auto issue_coef_slot = [&](int g, int slot) {  // lane 0 only: one box = RG rows x {a,b,c} x 128 columns
-        const uint32_t bar = bar0 + 8u * slot;
+        const uint32_t bar = cbar_of(slot);
         mbar_expect_tx(bar, (uint32_t)RG * CROW);
         tma_load_4d(sa32 + (uint32_t)slot * RG * CROW, &tm_c, x0, 0, g * RG, A.z_c0 + z, bar);
     };
     auto issue_uv_slot = [&](int g, int slot) {    // lane 0 only: one box = RG rows x {u,v} x 128 columns
-        const uint32_t bar = bar0 + 8u * (NGC + slot);
+        const uint32_t bar = ubar_of(slot);
         mbar_expect_tx(bar, (uint32_t)RG * UROW);
         tma_load_4d(su32 + (uint32_t)slot * RG * UROW, &tm_uv, x0, 0, g * RG, A.z_in0 + z, bar);
     };
@@ -182,10 +196,10 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         // "parity = round & 1" holds for every slot.
 #pragma unroll
         for (int k = 0; k < NGC; ++k)
-            if (k < s0) mbar_arrive(bar0 + 8u * k);
+            if (k < s0) mbar_arrive(cbar_of(k));
 #pragma unroll
         for (int k = 0; k < NGUV; ++k)
-            if (s0 > k && (((s0 - k + NGUV - 1) / NGUV) & 1)) mbar_arrive(bar0 + 8u * (NGC + k));
+            if (s0 > k && (((s0 - k + NGUV - 1) / NGUV) & 1)) mbar_arrive(ubar_of(k));
 #pragma unroll
         for (int k = 0; k < NGUV; ++k)
             if (g0 + k <= glast) issue_uv(g0 + k);
@@ -238,17 +252,14 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     };
 
     // one stage-row in steady state: time step S of one row (cu, cv) -> time step S+1 of the row
-    // above it, written back into cu, cv.  coff = byte offset of that row's coefficients.
-    auto stage_row = [&](auto edge_tag, auto s_tag, float (&cu)[4], float (&cv)[4], const int coff) {
+    // above it, written back into cu, cv.  ka, kb, kc = this lane's coefficients of that row.
+    auto stage_row = [&](auto edge_tag, auto s_tag, float (&cu)[4], float (&cv)[4], const float4& ka, const float4& kb, const float4& kc) {
         constexpr bool EDGE = decltype(edge_tag)::value;
         constexpr int S = decltype(s_tag)::value;
         if (EDGE && wmis) { sanitize_right(cu, col0, W); sanitize_right(cv, col0, W); }
         float lu = __shfl_up_sync(kFull, cu[3], 1), ru = __shfl_down_sync(kFull, cu[0], 1);
         float lv = __shfl_up_sync(kFull, cv[3], 1), rv = __shfl_down_sync(kFull, cv[0], 1);
         if (EDGE) { clamp_lr(cu, col0, W, lu, ru); clamp_lr(cv, col0, W, lv, rv); }
-        const float4 ka = *reinterpret_cast<const float4*>(sa_l + coff);
-        const float4 kb = *reinterpret_cast<const float4*>(sa_l + ROWB + coff);
-        const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * ROWB + coff);
         f32x2 hu[2], hv[2], ub[2], vb[2];
         hsum4(cu, lu, ru, hu);
         hsum4(cv, lv, rv, hv);
@@ -272,8 +283,8 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         if (r <= H - 1) {
             if ((rr % RG) == 0 || r == rs) {       // first row consumed from this group
                 const int gr = rr / RG;
-                mbar_wait(bar0 + 8u * (NGC + gr % NGUV), (gr / NGUV) & 1);
-                mbar_wait(bar0 + 8u * (gr % NGC), (gr / NGC) & 1);
+                mbar_wait(ubar_of(gr % NGUV), (gr / NGUV) & 1);
+                mbar_wait(cbar_of(gr % NGC), (gr / NGC) & 1);
             }
             const int q = (rr % NRUV) * UROW;
             const float4 tu = *reinterpret_cast<const float4*>(su_l + q);
@@ -354,90 +365,90 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     };
 
     // ---- steady state -------------------------------------------------------------------------------
-    // Both loops run with all T stages active and no run-time predicates on rows.  Output row of tick r is
-    // r - T; it is stored when 0 <= r - T - R0 < R1 - R0 (one unsigned compare, lanes of the halo excluded).
+    // All T stages active, no run-time predicates on rows.  One trip = RG ticks = one TMA row group of u/v consumed.
+    // Every shared-memory address of a trip is "register + compile-time constant": the loop keeps one pointer per
+    // coefficient group in use (kg[k] = group of the trip minus k, k = 0..DRET) and one for the current u/v slot, and
+    // rotates them once per trip; barrier addresses, phases and TMA coordinates advance incrementally.
+    // Output row of tick r is r - T; it is stored when 0 <= r - T - R0 < R1 - R0 (one unsigned compare, lanes of
+    // the halo excluded).
     const unsigned out_rows = lane_out ? (unsigned)(R1 - R0) : 0u;
-    float* uo_row = uo;                                         // advanced by one row per tick
-    float* vo_row = vo;
-    auto tick_body = [&](auto edge_tag, const int ubyte, auto coff_of, const int ro) {
-        float cu[4], cv[4];
-        const float4 tu = *reinterpret_cast<const float4*>(su_l + ubyte);
-        const float4 tv = *reinterpret_cast<const float4*>(su_l + ubyte + ROWB);
-        cu[0] = tu.x; cu[1] = tu.y; cu[2] = tu.z; cu[3] = tu.w;
-        cv[0] = tv.x; cv[1] = tv.y; cv[2] = tv.z; cv[3] = tv.w;
-        // stage S consumes row (r-S) and needs the coefficients of row (r-S-1)
-        [&]<int... S>(std::integer_sequence<int, S...>) {
-            (stage_row(edge_tag, std::integral_constant<int, S>{}, cu, cv, coff_of(S + 1)), ...);
-        }(std::make_integer_sequence<int, T>{});
-        if ((unsigned)(ro - R0) < out_rows) {
-            *reinterpret_cast<float4*>(uo_row) = make_float4(cu[0], cu[1], cu[2], cu[3]);
-            *reinterpret_cast<float4*>(vo_row) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            if constexpr (PEER) { if (push_any) push_row(ro, cu, cv); }
-        }
-        uo_row += A.row_pitch; vo_row += A.row_pitch;
-    };
-
-    // (a) main loop, strips that touch no image edge: one whole coefficient-ring period (NGC row groups = NRC
-    //     ticks) per trip, fully unrolled -- ring rows, barrier slots and the u/v barrier parities are constants.
-    constexpr int DRET = (T + RG - 1) / RG;                     // a coefficient group retires DRET groups after its first use
-    auto steady_period = [&](int r, const int r_end) {          // (r - base) is a multiple of NRC; returns the next tick
-        int grow = (r - base) / RG;                             // virtual group index, multiple of NGC
-        uint32_t cpar = (grow / NGC) & 1, upar = (grow / NGUV) & 1;
-        uo_row = uo + (size_t)(r - T) * A.row_pitch;
-        vo_row = vo + (size_t)(r - T) * A.row_pitch;
-#pragma unroll 1
-        for (; r + NRC - 1 <= r_end; r += NRC) {
-#pragma unroll
-            for (int q = 0; q < NGC; ++q) {
-                mbar_wait(bar0 + 8u * (NGC + q % NGUV), upar ^ ((q / NGUV) & 1));
-                mbar_wait(bar0 + 8u * q, cpar);
-#pragma unroll
-                for (int j = 0; j < RG; ++j) {
-                    const int cr = q * RG + j;                  // ring row of this tick (compile-time)
-                    tick_body(std::false_type{}, (cr % NRUV) * UROW, [&](int lag) { return ((cr - lag + NRC) % NRC) * CROW; }, r + cr - T);
-                }
-                __syncwarp();
-                if (lane == 0) {                                // refill the u/v slot just drained and the coefficient slot just retired
-                    const int gabs = g0v + grow + q;
-                    if (gabs + NGUV <= glast) issue_uv_slot(gabs + NGUV, q % NGUV);
-                    if (gabs - DRET + NGC <= glast) issue_coef_slot(gabs - DRET + NGC, (q - DRET + NGC) % NGC);
-                }
-            }
-            grow += NGC;
-            cpar ^= 1;
-            if ((NGC / NGUV) & 1) upar ^= 1;
-        }
-        return r;
-    };
-
-    // (b) rolled loop, one row group per trip: edge strips, and the groups left over by (a)
     auto steady = [&](auto edge_tag, int r, const int r_end) {   // r group-aligned; returns the next tick
-        const int rr0 = r - base;
-        int grow = rr0 / RG;                                   // virtual group index of the current tick
-        int urow = rr0 % NRUV, crow = rr0 % NRC;              // ring row of the current tick
-        int uslot = grow % NGUV, upar = (grow / NGUV) & 1, cslot = grow % NGC, cpar = (grow / NGC) & 1;
-        int gfin = grow - DRET;                                // coefficient group retired when the current group ends
-        uo_row = uo + (size_t)(r - T) * A.row_pitch;
-        vo_row = vo + (size_t)(r - T) * A.row_pitch;
+        const int grow = (r - base) / RG;                      // virtual group index of the first trip (>= DRET)
+        const uint32_t sa_l32 = sa32 + lane * 16, su_l32 = su32 + lane * 16;
+        uint32_t kg[DRET + 1];                                 // shared-memory address (this lane's 16 bytes) of group -k
+#pragma unroll
+        for (int k = 0; k <= DRET; ++k) kg[k] = sa_l32 + ((grow - k) % NGC) * (RG * CROW);
+        uint32_t up = su_l32 + (grow % NGUV) * (RG * UROW);
+        uint32_t ubar = ubar_of(grow % NGUV), upar = (uint32_t)(grow / NGUV) & 1u;
+        int cslot = grow % NGC;
+        uint32_t cbar = cbar_of(cslot), cpar = (uint32_t)(grow / NGC) & 1u;
+        // refills (lane 0): next u/v group -> the slot just drained; next coefficient group -> the slot retired
+        int uy = (g0v + grow + NGUV) * RG;                     // first row of the next u/v group to request
+        int cy = (g0v + grow - DRET + NGC) * RG;               // ... of the next coefficient group
+        int fslot = (grow - DRET) % NGC;                       // slot that retires at the end of this trip
+        const int ylast = glast * RG;
+        const int cymin = (g0 + NGC) * RG;                     // earlier groups were requested by the prologue
+        float* uo_row = uo + (size_t)(r - T) * A.row_pitch;    // advanced by one row per tick
+        float* vo_row = vo + (size_t)(r - T) * A.row_pitch;
+        unsigned orow = (unsigned)(r - T - R0);                // output row of the tick relative to the chunk
 #pragma unroll 1
         for (; r + RG - 1 <= r_end; r += RG) {
-            mbar_wait(bar0 + 8u * (NGC + uslot), upar);
-            mbar_wait(bar0 + 8u * cslot, cpar);
-#pragma unroll
-            for (int j = 0; j < RG; ++j) {
-                const int ur = wrap_up<NRUV>(urow + j), cr = wrap_up<NRC>(crow + j);
-                tick_body(edge_tag, ur * UROW, [&](int lag) { return wrap_down<NRC>(cr - lag) * CROW; }, r + j - T);
-            }
-            urow = wrap_up<NRUV>(urow + RG);
-            crow = wrap_up<NRC>(crow + RG);
+            mbar_wait(ubar, upar);
+            mbar_wait(cbar, cpar);
+            auto tick = [&](auto j_tag) {
+                constexpr int J = decltype(j_tag)::value;
+                float cu[4], cv[4];
+                const float4 tu = lds128<J * UROW>(up);
+                const float4 tv = lds128<J * UROW + ROWB>(up);
+                cu[0] = tu.x; cu[1] = tu.y; cu[2] = tu.z; cu[3] = tu.w;
+                cv[0] = tv.x; cv[1] = tv.y; cv[2] = tv.z; cv[3] = tv.w;
+                // stage S consumes row (r + J - S) and needs the coefficients of row (r + J - S - 1): row
+                // J - S - 1 relative to the first row of the trip's group, i.e. row REL + K*RG of group -K
+                auto stage = [&](auto s_tag) {
+                    constexpr int S = decltype(s_tag)::value;
+                    constexpr int REL = J - S - 1;
+                    constexpr int K = REL >= 0 ? 0 : (-REL + RG - 1) / RG;
+                    constexpr int OFF = (REL + K * RG) * CROW;
+                    const float4 ka = lds128<OFF>(kg[K]), kb = lds128<OFF + ROWB>(kg[K]), kc = lds128<OFF + 2 * ROWB>(kg[K]);
+                    stage_row(edge_tag, s_tag, cu, cv, ka, kb, kc);
+                };
+                [&]<int... S>(std::integer_sequence<int, S...>) {
+                    (stage(std::integral_constant<int, S>{}), ...);
+                }(std::make_integer_sequence<int, T>{});
+                if (orow + J < out_rows) {
+                    *reinterpret_cast<float4*>(uo_row) = make_float4(cu[0], cu[1], cu[2], cu[3]);
+                    *reinterpret_cast<float4*>(vo_row) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                    if constexpr (PEER) { if (push_any) push_row(r + J - T, cu, cv); }
+                }
+                uo_row += A.row_pitch; vo_row += A.row_pitch;
+            };
+            [&]<int... J>(std::integer_sequence<int, J...>) {
+                (tick(std::integral_constant<int, J>{}), ...);
+            }(std::make_integer_sequence<int, RG>{});
+            orow += RG;
             __syncwarp();
             if (lane == 0) {
-                if (g0v + grow + NGUV <= glast) issue_uv(g0v + grow + NGUV);
-                if (gfin >= s0 && g0v + gfin + NGC <= glast) issue_coef(g0v + gfin + NGC);
+                if (uy <= ylast) {
+                    mbar_expect_tx(ubar, (uint32_t)RG * UROW);
+                    tma_load_4d(up, &tm_uv, x0, 0, uy, A.z_in0 + z, ubar);   // lane 0: up is the slot base
+                }
+                if ((unsigned)(cy - cymin) <= (unsigned)(ylast - cymin) && ylast >= cymin) {
+                    const uint32_t fbar = cbar_of(fslot);
+                    mbar_expect_tx(fbar, (uint32_t)RG * CROW);
+                    tma_load_4d(kg[DRET], &tm_c, x0, 0, cy, A.z_c0 + z, fbar);
+                }
             }
-            ++grow; ++gfin;
-            if (++uslot == NGUV) { uslot = 0; upar ^= 1; }
-            if (++cslot == NGC) { cslot = 0; cpar ^= 1; }
+            uy += RG; cy += RG;
+            if (++fslot == NGC) fslot = 0;
+            // rotate: the u/v slot toggles (its phase flips when slot 1 -> 0), the coefficient groups age by one
+            upar ^= (ubar >> 3) & 1u;                          // ubar_of(1) = bar0 + 8 (bar0 is 128-byte aligned)
+            ubar ^= 8u;
+            up = (up == su_l32) ? su_l32 + RG * UROW : su_l32;
+#pragma unroll
+            for (int k = DRET; k > 0; --k) kg[k] = kg[k - 1];
+            if (++cslot == NGC) { cslot = 0; cpar ^= 1u; }
+            cbar = cbar_of(cslot);
+            kg[0] = sa_l32 + cslot * (RG * CROW);
         }
         return r;
     };
@@ -453,7 +464,6 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         if (edge) {
             r = steady(std::true_type{}, r, st_end);
         } else {
-            if constexpr (DefaultCfg<T>::PERIOD_UNROLL) r = steady_period(r, st_end);
             r = steady(std::false_type{}, r, st_end);
         }
         gen_end = last_tick + 1;                                 // bottom edge / remainder: generic ticks

@@ -85,7 +85,7 @@ struct hsflow {
     uint8_t* d_mask = nullptr;
     int* d_count = nullptr;
     size_t mask_cap = 0;
-    CUtensorMap tm_uvA, tm_uvB, tm_c;
+    CUtensorMap tm_uvA[3], tm_uvB[3], tm_c[3];     // [m]: TMA boxes of m + 2 rows (stream_geometry(T).rows_per_box = 2, 3, 4)
     // state
     int cur = 0;                                   // 0: uA/vA hold the current field, 1: uB/vB
     int valid_lo = 0, valid_hi = 0;
@@ -135,12 +135,12 @@ static bool use_stream_kernel(const hsflow* h, int t) {
     return t >= 2 || h->kernel_sel == 2 || h->connected;   // the peer transport lives in the streaming kernel
 }
 
-// 4-D map {W, planes, H, pairs} over a row-interleaved buffer; box = 128 columns x all planes x RG rows
-static int make_map(hsflow* h, CUtensorMap* tm, float* base, int planes, int pairs) {
+// 4-D map {W, planes, H, pairs} over a row-interleaved buffer; box = 128 columns x all planes x box_rows rows
+static int make_map(hsflow* h, CUtensorMap* tm, float* base, int planes, int pairs, int box_rows) {
     cuuint64_t dims[4] = {(cuuint64_t)h->W, (cuuint64_t)planes, (cuuint64_t)h->H, (cuuint64_t)pairs};
     cuuint64_t strides[3] = {(cuuint64_t)h->pitch * 4, (cuuint64_t)h->pitch * planes * 4,
                              (cuuint64_t)h->pitch * planes * h->H * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kStripW, (cuuint32_t)planes, (cuuint32_t)kStreamRowsPerBox, 1};
+    cuuint32_t box[4] = {(cuuint32_t)kStripW, (cuuint32_t)planes, (cuuint32_t)box_rows, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -303,10 +303,13 @@ int hsflow_configure(hsflow_t* h, int W, int H, int P) {
     }
     h->vA = h->uA + h->pitch; h->vB = h->uB + h->pitch;
     h->c1 = h->c0 + h->pitch; h->c2 = h->c0 + 2 * h->pitch;
-    int rc;
-    if ((rc = make_map(h, &h->tm_uvA, h->uA, 2, P)) || (rc = make_map(h, &h->tm_uvB, h->uB, 2, h->S)) ||
-        (rc = make_map(h, &h->tm_c, h->c0, 3, h->S)))
-        return rc;
+    for (int m = 0; m < 3; ++m) {
+        const int box_rows = m + 2;
+        int rc;
+        if ((rc = make_map(h, &h->tm_uvA[m], h->uA, 2, P, box_rows)) || (rc = make_map(h, &h->tm_uvB[m], h->uB, 2, h->S, box_rows)) ||
+            (rc = make_map(h, &h->tm_c[m], h->c0, 3, h->S, box_rows)))
+            return rc;
+    }
     CK(cudaMemsetAsync(h->uA, 0, uvP, h->stream));
     h->cur = 0; h->valid_lo = 0; h->valid_hi = H;
     return HSFLOW_OK;
@@ -468,7 +471,9 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
             A.flag_dn = h->has_peer[1] ? (unsigned*)h->peer[1][2] + 0 : nullptr;   // we are its upper neighbour
             A.epoch = h->epoch;
         }
-        CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uvA : h->tm_uvB, h->tm_c, A, n, wpc, h->stream));
+        const int m = G.rows_per_box - 2;
+        if (m < 0 || m > 2) return fail(HSFLOW_EINVAL, "internal: no tensor map for %d-row boxes", G.rows_per_box);
+        CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uvA[m] : h->tm_uvB[m], h->tm_c[m], A, n, wpc, h->stream));
         h->launches++;
         return HSFLOW_OK;
     }

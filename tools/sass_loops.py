@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """List the loops (backward branches) of one kernel in an object file with their instruction mix.
-    python tools/sass_loops.py opticalflowhs_b200/build/hs_stream.o 'k_jacobi_streamILi4ELi0' [min_len]"""
+    python tools/sass_loops.py opticalflowhs_b200/build/hs_stream_t4.o 'k_jacobi_streamILi4ELi0ELb0' [min_len] [max_len]
+Only innermost candidates are interesting: pass max_len to hide the enclosing loops."""
 import collections
 import re
 import subprocess
@@ -8,6 +9,7 @@ import sys
 
 obj, pat = sys.argv[1], sys.argv[2]
 minlen = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+maxlen = int(sys.argv[4]) if len(sys.argv) > 4 else 10 ** 9
 names = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
 cur, ins = None, []
 for l in names.splitlines():
@@ -25,7 +27,7 @@ for i, (a, t) in enumerate(ins):
     m = re.search(r"BRA.*0x([0-9a-f]+)", t)
     if m:
         tgt = int(m.group(1), 16)
-        if tgt < a and tgt in addr and i - addr[tgt] + 1 >= minlen:
+        if tgt < a and tgt in addr and minlen <= i - addr[tgt] + 1 <= maxlen:
             c = collections.Counter()
             for _, x in ins[addr[tgt]:i + 1]:
                 x = re.sub(r"^@!?U?P\d+\s+", "", x)
