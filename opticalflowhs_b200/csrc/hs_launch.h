@@ -79,6 +79,7 @@ cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long l
 
 // temporally blocked streaming kernel (hs_stream.cu)
 constexpr int kMaxT = 8;
+constexpr int kDefaultT = 6;           // temporal_block = 0: fastest sustained depth on B200 (profiles/README.md, T sweep)
 StreamGeom stream_geometry(int T);
 cudaError_t stream_prepare(int device);     // opt in to large dynamic shared memory for every instantiation
 int stream_warps_per_sm(int T, int stencil, int warps_per_cta);   // resident warps per SM (occupancy API)

@@ -127,7 +127,7 @@ static void free_planes(hsflow* h) {
 
 static int effective_T(const hsflow* h) {
     if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1) return 1;
-    int T = h->tblock > 0 ? h->tblock : 4;
+    int T = h->tblock > 0 ? h->tblock : kDefaultT;
     return std::min(T, kMaxT);
 }
 static bool use_stream_kernel(const hsflow* h, int t) {
