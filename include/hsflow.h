@@ -76,6 +76,12 @@ int hsflow_set_math(hsflow_t* h, int math_mode);          /* HSFLOW_MATH_*      
 int hsflow_set_deriv(hsflow_t* h, int deriv_mode);        /* HSFLOW_DERIV_*                     */
 int hsflow_set_tuning(hsflow_t* h, int chunk_rows, int warps_per_cta, int sub_batch); /* 0 = auto */
 int hsflow_set_warm_start(hsflow_t* h, int keep_uv);      /* use_previous (cv.h:481-483)        */
+/* The EPS half of cvTermCriteria(CV_TERMCRIT_ITER | CV_TERMCRIT_EPS, it, 1e-6) (OpticalFlowOpenCV.cpp:29,
+ * 94): every pair stops after the first sweep whose max |new - old| over u and v is < eps, or after
+ * `iterations` sweeps.  eps <= 0 (default) = ITER only, as runCLKernels (cpp:750-751).  While eps > 0 the
+ * iteration runs one fused sweep per launch with an in-kernel max-norm reduction and a device-side
+ * stop word per pair (no host round trip); not available in strip mode. */
+int hsflow_set_epsilon(hsflow_t* h, double eps);
 /* 0 = auto; 1 = single-sweep kernel only (one launch per iteration); 2 = streaming kernel even for T = 1 */
 int hsflow_set_kernel(hsflow_t* h, int which);
 
@@ -148,6 +154,8 @@ int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w
 /* ---- instrumentation ------------------------------------------------------------------ */
 float hsflow_last_ms(hsflow_t* h, int phase);         /* CUDA-event time of the last call's phase  */
 long long hsflow_kernel_launches(hsflow_t* h);        /* kernels launched by this handle so far    */
+int hsflow_iterations_done(hsflow_t* h, int pair, int* done);  /* sweeps a pair ran since prepare (< iterations
+                                                                   when hsflow_set_epsilon stopped it).  sync */
 int hsflow_effective_temporal_block(hsflow_t* h);
 void* hsflow_alloc_pinned(size_t bytes);              /* cudaMallocHost / cudaFreeHost helpers     */
 void hsflow_free_pinned(void* p);

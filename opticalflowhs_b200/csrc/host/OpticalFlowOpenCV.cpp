@@ -1,8 +1,7 @@
 // OpticalFlowOpenCV.cpp -- drop-in for /root/reference/OpticalFlowHS/OpticalFlowOpenCV.cpp
 // ("cv.cpp" below) on the CUDA engine: cvSmooth(CV_BLUR 3x3) x2 + cvCalcOpticalFlowHS
-// (cv.cpp:27-29) = HSFLOW_DERIV_CV + HSFLOW_STENCIL_CV4 with rho = 1/lambda.  The EPS half of
-// the termination criterion (1e-6) never fires before `it` iterations on real frames; the
-// engine runs exactly `it` iterations.
+// (cv.cpp:27-29) = HSFLOW_DERIV_CV + HSFLOW_STENCIL_CV4 with rho = 1/lambda and the same
+// termination criterion, CV_TERMCRIT_ITER | CV_TERMCRIT_EPS with eps = 1e-6 (hsflow_set_epsilon).
 #include "../../../include/OpticalFlowOpenCV.hpp"
 
 #include <chrono>
@@ -42,6 +41,7 @@ int OpticalFlowOpenCV::runFromImg(char* input1, char* input2, char* output, floa
     hsflow_set_deriv(e, HSFLOW_DERIV_CV);
     hsflow_set_params(e, 0.f, it, HSFLOW_STENCIL_CV4, 1, 0);
     hsflow_set_lambda(e, lambda);
+    hsflow_set_epsilon(e, 1e-6);                                            // cv.cpp:29 cvTermCriteria(ITER | EPS, it, 1e-6)
     const auto t0 = std::chrono::steady_clock::now();                       // cv.cpp:26
     int rc = hsflow_load_pair_gray8(e, a.data(), b.data(), w, h, 0);
     if (rc == HSFLOW_OK) rc = hsflow_compute(e);

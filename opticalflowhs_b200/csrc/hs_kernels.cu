@@ -171,7 +171,7 @@ __device__ __forceinline__ Row load_row(const float* __restrict__ plane, long lo
 }
 __device__ __forceinline__ float nb(const Row& R, int j) { return j < 0 ? R.l : (j > 3 ? R.r : R.c[j]); }
 
-template <bool EXACT, int ST, bool UPDATE_V>
+template <bool EXACT, int ST, bool UPDATE_V, bool TRACK>
 __global__ void __launch_bounds__(128) k_jacobi1(Jacobi1Args A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col0 = ((blockIdx.x * 4 + warp) * 32 + lane) * 4;
@@ -187,6 +187,15 @@ __global__ void __launch_bounds__(128) k_jacobi1(Jacobi1Args A) {
     const float* c1 = A.c1 + (size_t)z * A.c_pair_pitch;
     const float* c2 = A.c2 + (size_t)z * A.c_pair_pitch;
     const bool inb = col0 < A.W;
+    bool copy_only = false;                                    // TRACK: a converged pair is carried over, not iterated
+    if (TRACK) {
+        const int st = A.stop[z];
+        if (st) {
+            if (!A.last_sweep || ((st ^ A.total_sweeps) & 1) == 0) return;
+            copy_only = true;
+        }
+    }
+    float emax = 0.f;
 
     Row um = load_row(ui, A.row_pitch, R0 - 1, A.H, col0, A.W, lane);
     Row vm = load_row(vi, A.row_pitch, R0 - 1, A.H, col0, A.W, lane);
@@ -227,6 +236,11 @@ __global__ void __launch_bounds__(128) k_jacobi1(Jacobi1Args A) {
                 update_fast(ub, vb, ka[j], kb[j], kc[j], un[j], vn[j]);
             }
             if (!UPDATE_V) vn[j] = v0.c[j];                    // Kernels.cl:87-89: v is never written
+            if (TRACK) {
+                if (copy_only) { un[j] = u0.c[j]; vn[j] = v0.c[j]; }
+                else if (col0 + j < A.W)                       // Eps = max |new - old| (icvCalcOpticalFlowHS)
+                    emax = fmaxf(emax, fmaxf(fabsf(__fsub_rn(un[j], u0.c[j])), fabsf(__fsub_rn(vn[j], v0.c[j]))));
+            }
         }
         if (inb) {
             const size_t o = (size_t)rho * A.row_pitch + col0;
@@ -235,6 +249,22 @@ __global__ void __launch_bounds__(128) k_jacobi1(Jacobi1Args A) {
         }
         um = u0; vm = v0; u0 = up; v0 = vp;
     }
+    if (TRACK && !copy_only) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) emax = fmaxf(emax, __shfl_xor_sync(kFull, emax, d));
+        if (lane == 0 && emax > 0.f) atomicMax(A.emax + z, __float_as_uint(emax));
+    }
+}
+
+__global__ void k_eps_check(unsigned* emax, int* stop, double eps, int sweep, int pairs) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= pairs) return;
+    if (!stop[z] && (double)__uint_as_float(emax[z]) < eps) stop[z] = (sweep << 1) | (sweep & 1);
+    emax[z] = 0u;
+}
+__global__ void k_eps_settle(int* stop, int total, int pairs) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z < pairs && stop[z]) stop[z] = (stop[z] & ~1) | (total & 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -320,8 +350,17 @@ cudaError_t launch_deriv_cv(const DerivArgs& A, int pairs, cudaStream_t s) {
 }
 
 template <bool EXACT, int ST> static void launch_j1(const Jacobi1Args& A, bool upd, dim3 g, cudaStream_t s) {
-    if (upd) k_jacobi1<EXACT, ST, true><<<g, 128, 0, s>>>(A);
-    else k_jacobi1<EXACT, ST, false><<<g, 128, 0, s>>>(A);
+    const bool track = A.stop != nullptr;
+    if (upd) { if (track) k_jacobi1<EXACT, ST, true, true><<<g, 128, 0, s>>>(A); else k_jacobi1<EXACT, ST, true, false><<<g, 128, 0, s>>>(A); }
+    else     { if (track) k_jacobi1<EXACT, ST, false, true><<<g, 128, 0, s>>>(A); else k_jacobi1<EXACT, ST, false, false><<<g, 128, 0, s>>>(A); }
+}
+cudaError_t launch_eps_check(unsigned* emax, int* stop, double eps, int sweep, int pairs, cudaStream_t s) {
+    k_eps_check<<<(pairs + 127) / 128, 128, 0, s>>>(emax, stop, eps, sweep, pairs);
+    return cudaGetLastError();
+}
+cudaError_t launch_eps_settle(int* stop, int total, int pairs, cudaStream_t s) {
+    k_eps_settle<<<(pairs + 127) / 128, 128, 0, s>>>(stop, total, pairs);
+    return cudaGetLastError();
 }
 cudaError_t launch_jacobi1(const Jacobi1Args& A, bool exact, int stencil, bool update_v, int pairs, cudaStream_t s) {
     const int rows = A.out_hi - A.out_lo;

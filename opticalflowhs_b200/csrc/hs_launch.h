@@ -36,6 +36,14 @@ struct Jacobi1Args {
     int out_lo, out_hi;         // rows to produce
     int chunk_rows;
     float rho;                  // EXACT only
+    // Convergence tracking (hsflow_set_epsilon; the CV_TERMCRIT_EPS half of cv.cpp:29), nullptr = off.
+    // emax[pair]: max |new - old| of this sweep as float bits (atomicMax; non-negative floats order like uints).
+    // stop[pair]: 0 = still iterating, else (sweeps executed << 1) | parity of the buffer that holds the field.
+    // A stopped pair skips the sweep; the LAST sweep of a call copies it when it sits in the other buffer.
+    unsigned* emax;
+    int* stop;
+    int last_sweep;             // 1: final sweep of this hsflow_iterate / hsflow_compute call
+    int total_sweeps;           // sweeps since hsflow_prepare at the end of the call (parity of the final buffer)
 };
 
 struct StreamArgs {
@@ -72,6 +80,10 @@ cudaError_t launch_deriv(const DerivArgs& A, int fmt, int pairs, cudaStream_t s)
 cudaError_t launch_box3(const uint8_t* src, uint8_t* dst, int W, int H, long long rp, long long pp, int pairs, cudaStream_t s);
 cudaError_t launch_deriv_cv(const DerivArgs& A, int pairs, cudaStream_t s);
 cudaError_t launch_jacobi1(const Jacobi1Args& A, bool exact, int stencil, bool update_v, int pairs, cudaStream_t s);
+// after sweep number `sweep` (1-based since prepare): stop[z] = (sweep << 1) | (sweep & 1) where emax[z] < eps; emax[z] = 0
+cudaError_t launch_eps_check(unsigned* emax, int* stop, double eps, int sweep, int pairs, cudaStream_t s);
+// end of a call that ran up to `total` sweeps: every stopped pair now sits in the buffer of parity total & 1
+cudaError_t launch_eps_settle(int* stop, int total, int pairs, cudaStream_t s);
 cudaError_t launch_synth(uint8_t* f1, uint8_t* f2, int W, int rows, int full_h, int row0, long long rp, long long pp,
                          uint32_t seed0, int pairs, cudaStream_t s);
 cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long long pitch, int step, float thr,

@@ -102,6 +102,13 @@ struct hsflow {
     int push_lo[2] = {}, push_hi[2] = {}, push_delta[2] = {};
     int connected = 0;
     unsigned epoch = 0;
+    // EPS termination (hsflow_set_epsilon): per-pair device words, see Jacobi1Args
+    double eps = 0.0;
+    unsigned* d_emax = nullptr;
+    int* d_stop = nullptr;
+    int eps_cap = 0;                               // pairs the two arrays hold
+    int sweeps = 0;                                // sweeps since hsflow_prepare (hsflow_iterate path)
+    int ec_on = 0, ec_sweep = 0, ec_total = 0, ec_off = 0;   // tracking context of the sweep run_block launches next
 };
 
 static void strip_disconnect(hsflow* h) {
@@ -126,12 +133,12 @@ static void free_planes(hsflow* h) {
 }
 
 static int effective_T(const hsflow* h) {
-    if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1) return 1;
+    if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1 || h->eps > 0.0) return 1;
     int T = h->tblock > 0 ? h->tblock : kDefaultT;
     return std::min(T, kMaxT);
 }
 static bool use_stream_kernel(const hsflow* h, int t) {
-    if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1) return false;
+    if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1 || h->eps > 0.0) return false;
     return t >= 2 || h->kernel_sel == 2 || h->connected;   // the peer transport lives in the streaming kernel
 }
 
@@ -209,6 +216,7 @@ int hsflow_destroy(hsflow_t* h) {
     cudaStreamSynchronize(h->stream);
     free_planes(h);
     cudaFree(h->sig);
+    cudaFree(h->d_emax); cudaFree(h->d_stop);
     cudaFree(h->d_mask); cudaFree(h->d_count);
     for (int i = 0; i < 4; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -273,6 +281,35 @@ int hsflow_set_kernel(hsflow_t* h, int which) {   /* 0 auto, 1 single-sweep kern
     return HSFLOW_OK;
 }
 int hsflow_set_warm_start(hsflow_t* h, int keep) { NEED(h); h->warm = keep ? 1 : 0; return HSFLOW_OK; }
+int hsflow_set_epsilon(hsflow_t* h, double eps) {
+    NEED(h);
+    if (eps != eps) return fail(HSFLOW_EINVAL, "epsilon is NaN");
+    h->eps = eps > 0.0 ? eps : 0.0;
+    h->prepared = 0;
+    return HSFLOW_OK;
+}
+
+// EPS mode: the per-pair convergence words, zeroed ("every pair still iterating") for pairs [off, off + n)
+static int eps_reset(hsflow* h, int off, int n) {
+    if (h->eps_cap < h->P) {
+        cudaFree(h->d_emax); cudaFree(h->d_stop);
+        h->d_emax = nullptr; h->d_stop = nullptr; h->eps_cap = 0;
+        if (cudaMalloc(&h->d_emax, (size_t)h->P * sizeof(unsigned)) != cudaSuccess ||
+            cudaMalloc(&h->d_stop, (size_t)h->P * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(HSFLOW_ENOMEM, "cudaMalloc of the convergence words failed");
+        }
+        h->eps_cap = h->P;
+    }
+    CK(cudaMemsetAsync(h->d_emax + off, 0, (size_t)n * sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->d_stop + off, 0, (size_t)n * sizeof(int), h->stream));
+    return HSFLOW_OK;
+}
+static int eps_guard(const hsflow* h) {
+    if (h->eps > 0.0 && (!h->top_edge || !h->bottom_edge || h->connected))
+        return fail(HSFLOW_EINVAL, "the EPS criterion needs the whole frame on one device (not available in strip mode)");
+    return HSFLOW_OK;
+}
 
 int hsflow_configure(hsflow_t* h, int W, int H, int P) {
     NEED(h);
@@ -489,8 +526,17 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
     A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
     A.chunk_rows = h->chunk_rows > 0 ? h->chunk_rows : std::max(1, std::min(out_hi - out_lo, 64));
     A.rho = h->rho;
+    if (h->ec_on) {                                // EPS mode: track max |new - old|, carry converged pairs over
+        A.emax = h->d_emax + h->ec_off; A.stop = h->d_stop + h->ec_off;
+        A.last_sweep = h->ec_sweep == h->ec_total; A.total_sweeps = h->ec_total;
+    }
     CK(launch_jacobi1(A, h->math == HSFLOW_MATH_EXACT, h->stencil, h->update_v != 0, n, h->stream));
     h->launches++;
+    if (h->ec_on) {
+        CK(launch_eps_check(A.emax, A.stop, h->eps, h->ec_sweep, n, h->stream));
+        h->launches++;
+        if (A.last_sweep) { CK(launch_eps_settle(A.stop, h->ec_total, n, h->stream)); h->launches++; }
+    }
     return HSFLOW_OK;
 }
 
@@ -510,6 +556,8 @@ int hsflow_prepare(hsflow_t* h) {
     }
     phase_end(h, HSFLOW_PHASE_DERIV);
     h->valid_lo = 0; h->valid_hi = h->H;
+    h->sweeps = 0;
+    if (h->eps > 0.0) { if ((rc = eps_guard(h)) || (rc = eps_reset(h, 0, h->P))) return rc; }
     h->prepared = 1;
     return HSFLOW_OK;
 }
@@ -536,6 +584,7 @@ int hsflow_iterate(hsflow_t* h, int n) {
             int rc = run_block(h, t, h->cur, 0, h->P, lo, hi);
             if (rc) return rc;
             h->cur ^= 1;
+            h->sweeps += t;
             for (int d = 0; d < 2; ++d)
                 if (h->has_peer[d]) {
                     CUresult r = h->wait_value((CUstream)h->stream, (CUdeviceptr)(h->sig + d), h->epoch, CU_STREAM_WAIT_VALUE_GEQ);
@@ -547,6 +596,8 @@ int hsflow_iterate(hsflow_t* h, int n) {
         phase_end(h, HSFLOW_PHASE_ITER);
         return HSFLOW_OK;
     }
+    const int sweeps_at_end = h->sweeps + n;
+    { int rc = eps_guard(h); if (rc) return rc; }
     while (n > 0) {
         const int t = std::min(n, T);
         const int lo = h->top_edge ? 0 : h->valid_lo + t;
@@ -557,13 +608,17 @@ int hsflow_iterate(hsflow_t* h, int n) {
             int rc = run_block(h, t, h->cur, 0, h->P, lo, hi);
             if (rc) return rc;
             h->cur ^= 1;
+            h->sweeps += t;
         } else {
             for (int k = 0; k < t; ++k) {
                 const int lo1 = h->top_edge ? 0 : h->valid_lo + k + 1;
                 const int hi1 = h->bottom_edge ? h->H : h->valid_hi - k - 1;
+                h->ec_on = h->eps > 0.0; h->ec_sweep = h->sweeps + 1; h->ec_total = sweeps_at_end; h->ec_off = 0;
                 int rc = run_block(h, 1, h->cur, 0, h->P, lo1, hi1);
+                h->ec_on = 0;
                 if (rc) return rc;
                 h->cur ^= 1;
+                h->sweeps++;
             }
         }
         h->valid_lo = lo; h->valid_hi = hi;
@@ -589,6 +644,8 @@ static int compute_subbatch(hsflow* h, int p0, int n) {
     int src = (L % 2 == 0) ? 0 : 1;                // so that the last flip lands in A
     float* uv = src == 0 ? h->uA + (size_t)p0 * h->uv_pp : h->uB;
     CK(cudaMemsetAsync(uv, 0, (size_t)h->uv_pp * n * sizeof(float), h->stream));   // cpp:331-332
+    int sweep = 0;
+    if (h->eps > 0.0 && (rc = eps_reset(h, p0, n))) return rc;
     for (int left = N; left > 0;) {
         const int t = std::min(left, T);
         if (use_stream_kernel(h, t)) {
@@ -596,7 +653,13 @@ static int compute_subbatch(hsflow* h, int p0, int n) {
             if (rc) return rc;
             src ^= 1;
         } else {
-            for (int k = 0; k < t; ++k) { rc = run_block(h, 1, src, p0, n, 0, h->H); if (rc) return rc; src ^= 1; }
+            for (int k = 0; k < t; ++k) {
+                h->ec_on = h->eps > 0.0; h->ec_sweep = ++sweep; h->ec_total = N; h->ec_off = p0;
+                rc = run_block(h, 1, src, p0, n, 0, h->H);
+                h->ec_on = 0;
+                if (rc) return rc;
+                src ^= 1;
+            }
         }
         left -= t;
     }
@@ -614,6 +677,8 @@ int hsflow_compute(hsflow_t* h) {
     // batch larger than the scratch: sub-batches of S pairs; results always end in the A planes
     if (h->warm) return fail(HSFLOW_EINVAL, "warm start needs pairs <= sub_batch");
     CK(cudaSetDevice(h->device));
+    { int rc = eps_guard(h); if (rc) return rc; }
+    h->sweeps = h->iterations;
     phase_begin(h, HSFLOW_PHASE_ITER);
     for (int p0 = 0; p0 < h->P; p0 += h->S) {
         int rc = compute_subbatch(h, p0, std::min(h->S, h->P - p0));
@@ -875,6 +940,18 @@ float hsflow_last_ms(hsflow_t* h, int phase) {
     return ms;
 }
 long long hsflow_kernel_launches(hsflow_t* h) { return h ? h->launches : 0; }
+int hsflow_iterations_done(hsflow_t* h, int pair, int* done) {
+    NEED(h);
+    if (pair < 0 || pair >= h->P || !done) return fail(HSFLOW_EINVAL, "bad argument");
+    *done = h->sweeps;
+    if (h->eps > 0.0 && h->d_stop && pair < h->eps_cap) {
+        int st = 0;
+        CK(cudaMemcpyAsync(&st, h->d_stop + pair, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (st) *done = st >> 1;
+    }
+    return HSFLOW_OK;
+}
 int hsflow_effective_temporal_block(hsflow_t* h) { return h ? effective_T(h) : 0; }
 
 void* hsflow_alloc_pinned(size_t bytes) {

@@ -41,6 +41,7 @@ SIGNATURES = {
     "hsflow_set_deriv": (C.c_int, [_P, C.c_int]),
     "hsflow_set_tuning": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "hsflow_set_warm_start": (C.c_int, [_P, C.c_int]),
+    "hsflow_set_epsilon": (C.c_int, [_P, C.c_double]),
     "hsflow_set_kernel": (C.c_int, [_P, C.c_int]),
     "hsflow_configure": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "hsflow_set_strip": (C.c_int, [_P, C.c_int, C.c_int]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "hsflow_run_batch_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hsflow_last_ms": (C.c_float, [_P, C.c_int]),
     "hsflow_kernel_launches": (C.c_longlong, [_P]),
+    "hsflow_iterations_done": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "hsflow_effective_temporal_block": (C.c_int, [_P]),
     "hsflow_alloc_pinned": (_P, [C.c_size_t]),
     "hsflow_free_pinned": (None, [_P]),
@@ -148,6 +150,15 @@ class HSFlow:
 
     def set_warm_start(self, keep):
         self._ck(self._L.hsflow_set_warm_start(self._h, int(keep))); return self
+
+    def set_epsilon(self, eps):
+        """EPS termination of cvCalcOpticalFlowHS (cv.cpp:29): stop a pair once max |new - old| < eps; 0 = off."""
+        self._ck(self._L.hsflow_set_epsilon(self._h, float(eps))); return self
+
+    def iterations_done(self, pair=0):
+        n = C.c_int(0)
+        self._ck(self._L.hsflow_iterations_done(self._h, pair, C.byref(n)))
+        return n.value
 
     def set_stream(self, cuda_stream):
         self._ck(self._L.hsflow_set_stream(self._h, C.c_void_p(cuda_stream or 0))); return self

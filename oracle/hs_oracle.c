@@ -68,13 +68,18 @@ static inline float avg8(const float* x, int w, int h, int i, int j, float we, f
                  tex(x, w, h, i + 1, j + 1));
 }
 
-int hso_jacobi_general(float* u, float* v, const float* Ex, const float* Ey, const float* Et,
-                       int w, int h, float we, float wd, float rho, int iterations, int update_v) {
+/* The iteration with the termination rule of cvCalcOpticalFlowHS (cv.cpp:29: CV_TERMCRIT_ITER | CV_TERMCRIT_EPS):
+ * stop after max_iter sweeps, or after the first sweep whose max |new - old| over u and v is < eps.
+ * eps <= 0: exactly max_iter sweeps (the Kernels.cl path, cpp:750-751).  Returns the sweeps executed. */
+int hso_jacobi_general_eps(float* u, float* v, const float* Ex, const float* Ey, const float* Et,
+                           int w, int h, float we, float wd, float rho, int iterations, double eps, int update_v) {
     size_t n = (size_t)w * h;
     float* ua = (float*)malloc(n * sizeof(float));
     float* va = (float*)malloc(n * sizeof(float));
     if (!ua || !va) { free(ua); free(va); return -1; }
-    for (int it = 0; it < iterations; ++it) {
+    int it = 0;
+    for (; it < iterations;) {
+        float emax = 0.f;
         /* u_v_avgKernel over the whole frame first (cpp:537-551) ... */
 #pragma omp parallel for schedule(static)
         for (int j = 0; j < h; ++j)
@@ -84,18 +89,33 @@ int hso_jacobi_general(float* u, float* v, const float* Ex, const float* Ey, con
                 va[pos] = avg8(v, w, h, i, j, we, wd);
             }
         /* ... then u_v_updateKernel (cpp:623-637), Kernels.cl:84-86. */
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) reduction(max : emax)
         for (int j = 0; j < h; ++j)
             for (int i = 0; i < w; ++i) {
                 size_t pos = (size_t)j * w + i;
                 float t = Ex[pos] * ua[pos] + Ey[pos] * va[pos] + Et[pos];
                 t /= rho + Ex[pos] * Ex[pos] + Ey[pos] * Ey[pos];
-                u[pos] = ua[pos] - Ex[pos] * t;
-                if (update_v) v[pos] = va[pos] - Ey[pos] * t; /* absent at Kernels.cl:87-89 */
+                float un = ua[pos] - Ex[pos] * t;
+                float du = fabsf(un - u[pos]);
+                if (du > emax) emax = du;
+                u[pos] = un;
+                if (update_v) { /* absent at Kernels.cl:87-89 */
+                    float vn = va[pos] - Ey[pos] * t;
+                    float dv = fabsf(vn - v[pos]);
+                    if (dv > emax) emax = dv;
+                    v[pos] = vn;
+                }
             }
+        ++it;
+        if (eps > 0 && (double)emax < eps) break;
     }
     free(ua); free(va);
-    return 0;
+    return it;
+}
+
+int hso_jacobi_general(float* u, float* v, const float* Ex, const float* Ey, const float* Et,
+                       int w, int h, float we, float wd, float rho, int iterations, int update_v) {
+    return hso_jacobi_general_eps(u, v, Ex, Ey, Et, w, h, we, wd, rho, iterations, 0.0, update_v) < 0 ? -1 : 0;
 }
 
 int hso_jacobi(float* u, float* v, const float* Ex, const float* Ey, const float* Et,

@@ -44,6 +44,12 @@ int hso_jacobi(float* u, float* v, const float* Ex, const float* Ey, const float
 int hso_jacobi_general(float* u, float* v, const float* Ex, const float* Ey, const float* Et,
                        int w, int h, float w_edge, float w_diag, float rho, int iterations, int update_v);
 
+/* hso_jacobi_general with the termination rule of cvCalcOpticalFlowHS (OpticalFlowOpenCV.cpp:29,
+ * CV_TERMCRIT_ITER | CV_TERMCRIT_EPS): at most `iterations` sweeps, stop after the first sweep whose
+ * max |new - old| over u and v is < eps (eps <= 0: never).  Returns the sweeps executed. */
+int hso_jacobi_general_eps(float* u, float* v, const float* Ex, const float* Ey, const float* Et,
+                           int w, int h, float w_edge, float w_diag, float rho, int iterations, double eps, int update_v);
+
 /* Whole CL path: gray u8 pair -> u, v (runDerivatives + iterations x runCLKernels, cpp:748-751). */
 int hso_run_cl(const uint8_t* g1, const uint8_t* g2, int w, int h, float alpha, int iterations,
                int update_v, float* u, float* v);

@@ -42,6 +42,8 @@ def lib():
         L.hso_jacobi.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
         L.hso_jacobi_general.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int,
                                          C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.hso_jacobi_general_eps.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int,
+                                             C.c_float, C.c_float, C.c_float, C.c_int, C.c_double, C.c_int]
         L.hso_run_cl.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _f32p, _f32p]
         L.hso_box3_u8.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
         L.hso_cvhs.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_double, C.c_int, _f32p, _f32p]
@@ -113,6 +115,16 @@ def jacobi_general(Ex, Ey, Et, w_edge, w_diag, rho, iterations, update_v=True, u
     lib().hso_jacobi_general(u, v, np.ascontiguousarray(Ex), np.ascontiguousarray(Ey), np.ascontiguousarray(Et),
                              w, h, w_edge, w_diag, rho, iterations, int(update_v))
     return u, v
+
+
+def jacobi_general_eps(Ex, Ey, Et, w_edge, w_diag, rho, max_iter, eps, update_v=True, u0=None, v0=None):
+    """jacobi_general with the ITER | EPS termination of cvCalcOpticalFlowHS (cv.cpp:29); returns u, v, sweeps executed."""
+    h, w = Ex.shape
+    u = np.zeros((h, w), np.float32) if u0 is None else np.array(u0, np.float32, order="C")
+    v = np.zeros((h, w), np.float32) if v0 is None else np.array(v0, np.float32, order="C")
+    it = lib().hso_jacobi_general_eps(u, v, np.ascontiguousarray(Ex), np.ascontiguousarray(Ey), np.ascontiguousarray(Et),
+                                      w, h, w_edge, w_diag, rho, max_iter, float(eps), int(update_v))
+    return u, v, it
 
 
 def run_cl(g1, g2, alpha, iterations, update_v=True):

@@ -324,6 +324,80 @@ def test_cv_mode_matches_restated_opencv_and_golden_masks(eng, P, oracle, frames
     eng.set_deriv(P.DERIV_CL)
 
 
+# ---- EPS termination: cvTermCriteria(CV_TERMCRIT_ITER | CV_TERMCRIT_EPS, it, eps), cv.cpp:29 ------------------
+
+def _weights(P, stencil):
+    if stencil == P.STENCIL_CL8:
+        return np.float32(1.0 / 6), np.float32(1.0 / 12), np.float32(15.0) * np.float32(15.0)
+    return np.float32(0.25), np.float32(0.0), np.float32(1.0) / np.float32(0.1)
+
+
+@pytest.mark.parametrize("stencil_name", ["cl8", "cv4"])
+def test_epsilon_stop_sweep_count_and_field_bitwise(eng, P, oracle, stencil_name):
+    stencil = P.STENCIL_CL8 if stencil_name == "cl8" else P.STENCIL_CV4
+    f1, f2 = oracle.synth_pair(160, 120, seed=3)
+    d = oracle.derivatives(f1.astype(np.float32), f2.astype(np.float32))
+    we, wd, rho = _weights(P, stencil)
+    seen = set()
+    for eps, max_iter in [(5e-2, 300), (5e-2, 301), (4e-3, 300), (4e-3, 301), (1e-12, 40), (0.0, 17)]:
+        uo, vo, it = oracle.jacobi_general_eps(*d, we, wd, rho, max_iter, eps, True)
+        eng.set_math(P.MATH_EXACT).set_params(15.0, max_iter, stencil, True)
+        if stencil == P.STENCIL_CV4:
+            eng.set_lambda(0.1)
+        eng.set_epsilon(eps).load_pair(f1, f2).compute()
+        u, v = eng.read_uv()
+        assert eng.iterations_done() == it, (eps, max_iter, eng.iterations_done(), it)
+        assert (bits(u) == bits(uo)).all() and (bits(v) == bits(vo)).all(), (eps, max_iter)
+        seen.add((it < max_iter, (max_iter - it) & 1))
+    assert {(True, 0), (True, 1), (False, 0)} <= seen      # stopped early in either buffer, and ran to the cap
+    eng.set_epsilon(0.0)
+
+
+def test_epsilon_stop_per_pair_in_batches_and_split_iterate(P, oracle):
+    W, H, n, max_iter, eps = 144, 80, 5, 260, 6e-3
+    frames, want = [], []
+    we, wd, rho = _weights(P, P.STENCIL_CL8)
+    for k in range(n):
+        f1, f2 = oracle.synth_pair(W, H, seed=40 + 7 * k)
+        if k == 3:
+            f2 = f1.copy()                              # no motion: converges after the first sweep
+        frames.append((f1, f2))
+        d = oracle.derivatives(f1.astype(np.float32), f2.astype(np.float32))
+        want.append(oracle.jacobi_general_eps(*d, we, wd, rho, max_iter, eps, True))
+    assert len({w[2] for w in want}) >= 3 and want[3][2] == 1
+    for sub in (0, 2):                                  # one sub-batch (prepare + iterate) / sub-batches of 2
+        with P.HSFlow(0) as e:
+            e.set_tuning(0, 0, sub).set_math(P.MATH_EXACT).set_params(15.0, max_iter, P.STENCIL_CL8, True).set_epsilon(eps)
+            e.configure(W, H, n)
+            for k, (f1, f2) in enumerate(frames):
+                e.set_frames(f1, f2, pair=k)
+            if sub == 0:                                # the split form: two iterate calls continue one session
+                e.prepare(); e.iterate(101); e.iterate(max_iter - 101); e.sync()
+            else:
+                e.compute()
+            for k in range(n):
+                u, v = e.read_uv(k)
+                assert (bits(u) == bits(want[k][0])).all() and (bits(v) == bits(want[k][1])).all(), (sub, k)
+                assert e.iterations_done(k) == want[k][2], (sub, k, e.iterations_done(k), want[k][2])
+
+
+def test_epsilon_stop_fast_math_and_strip_mode_refusal(eng, P, oracle):
+    f1, f2 = oracle.synth_pair(200, 96, seed=11)
+    d = oracle.derivatives(f1.astype(np.float32), f2.astype(np.float32))
+    we, wd, rho = _weights(P, P.STENCIL_CL8)
+    uo, vo, it = oracle.jacobi_general_eps(*d, we, wd, rho, 400, 3e-3, True)
+    eng.set_math(P.MATH_FAST).set_params(15.0, 400, P.STENCIL_CL8, True, 6).set_epsilon(3e-3)
+    assert eng.temporal_block == 1                      # EPS is checked after every sweep, as the reference does
+    eng.load_pair(f1, f2).compute()
+    u, v = eng.read_uv()
+    assert abs(eng.iterations_done() - it) <= 2 and it < 400
+    assert np.abs(u - uo).max() <= TOL_MAX and np.abs(v - vo).max() <= TOL_MAX
+    eng.set_strip(False, True)
+    with pytest.raises(P.HSFlowError):
+        eng.prepare()
+    eng.set_strip(True, True).set_epsilon(0.0)
+
+
 # ---- full-size frames: window check through the domain of dependence -----------------------------------------
 
 @pytest.mark.parametrize("W,H,N,T", [(3840, 2160, 100, 4), (3840, 2160, 100, 8), (1920, 1080, 200, 6)])
