@@ -125,6 +125,28 @@ def cpu_reference_rate(target_seconds, threads=None):
     return rate, cores, kind, sample, dt
 
 
+def cpu_opencv_rate(target_seconds):
+    """The reference's CPU comparator (OpticalFlowOpenCV.cpp:26-30: two 3x3 blurs + cvCalcOpticalFlowHS, restated in
+    oracle/hs_oracle.c because cv210.dll is a third-party Win32 binary) on one synthetic 4K pair: single thread, as
+    the legacy routine runs, and OpenMP over rows on all host cores."""
+    import oracle as O
+    O.build()
+    f1, f2 = O.synth_pair(W4K, H4K, seed=1234)
+    out = {"unit": UNIT, "kind": "port", "lambda": 0.1,
+           "what": "restated OpenCV 2.1 cvCalcOpticalFlowHS incl. both cvSmooth calls, 4-neighbour stencil, eps = 1e-6"}
+    for label, threads in (("one_thread", 1), ("all_threads", O.max_threads())):
+        O.set_threads(threads)
+        t0 = time.perf_counter(); O.run_cv(f1, f2, 0.1, 2, eps=1e-6); t2 = time.perf_counter() - t0
+        t0 = time.perf_counter(); O.run_cv(f1, f2, 0.1, 4, eps=1e-6); t4 = time.perf_counter() - t0
+        per_it = max((t4 - t2) / 2, 1e-4)
+        n = int(max(2, min(ITER, (target_seconds - t2) / per_it)))
+        t0 = time.perf_counter(); _, _, done = O.run_cv(f1, f2, 0.1, n, eps=1e-6); dt = time.perf_counter() - t0
+        out[label] = {"value": W4K * H4K * done / dt / 1e6, "cores": threads,
+                      "sample": f"1 synthetic {W4K}x{H4K} pair x {done} iterations (of {ITER}), {dt:.1f} s"}
+    O.set_threads(O.max_threads())
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -255,10 +277,11 @@ def run_ours(args, rank, world, local_rank):
     eng.close()
 
     if rank == 0:
-        cpu = None
+        cpu = cpu_cv = None
         if world == 1 and not args.no_cpu:
             rate, cores, kind, sample, _ = cpu_reference_rate(args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            cpu_cv = cpu_opencv_rate(args.cpu_seconds / 3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -274,6 +297,7 @@ def run_ours(args, rank, world, local_rank):
                          "note": "unfused-equivalent bytes (28 B/px-it x T per launch): frac > 1 is the temporal-blocking gain; "
                                  "ncu dram bytes are in profiles/"},
             "cpu_baseline": cpu,
+            "cpu_baseline_opencv": cpu_cv,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W4K * H4K * ep,
                     "d2h_bytes_per_step": 8 * W4K * H4K * ep, "pairs_per_step": ep, "api": "hsflow_run_batch_host",
                     "result_checksum": result_checksum},
