@@ -66,6 +66,12 @@ struct StreamArgs {
     int up_lo, up_hi, up_delta;
     int dn_lo, dn_hi, dn_delta;
     unsigned* done_counter;     // device word, 0 between launches; nullptr: no signalling
+    // seam_first = 1: the top and bottom row chunks are scheduled first and only they are counted (signal_units of
+    // them): the neighbours hear about this launch as soon as its seam rows are out, long before it ends, so the
+    // wait before the next launch is already satisfied.  Set by launch_jacobi_stream when all ghost-row reads and
+    // all pushes fall into those two chunks; otherwise every unit counts (signal_units = total_units).
+    int seam_first;
+    long long signal_units;
     unsigned* flag_up;          // word in the upper / lower neighbour's memory that receives `epoch`
     unsigned* flag_dn;
     unsigned epoch;
@@ -92,6 +98,7 @@ cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long l
 // temporally blocked streaming kernel (hs_stream.cu)
 constexpr int kMaxT = 8;
 constexpr int kDefaultT = 6;           // temporal_block = 0: fastest sustained depth on B200 (profiles/README.md, T sweep)
+constexpr int kSmallT = 4;             // ... when the job cannot fill the GPU twice over: shorter warm-up, shorter units
 StreamGeom stream_geometry(int T);
 cudaError_t stream_prepare(int device);     // opt in to large dynamic shared memory for every instantiation
 int stream_warps_per_sm(int T, int stencil, int warps_per_cta);   // resident warps per SM (occupancy API)

@@ -1,5 +1,7 @@
 // hs_stream.cu -- host-side dispatch of the temporally blocked streaming kernel (hs_stream.cuh).  The kernel is
 // instantiated per block depth T in hs_stream_inst.cu (one object per T).
+#include <algorithm>
+
 #include "hs_stream.cuh"
 
 namespace hs {
@@ -51,6 +53,19 @@ cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tuv, con
     A.nsx = (A.W + G.valid_w - 1) / G.valid_w;
     A.ncy = (rows + A.chunk_rows - 1) / A.chunk_rows;
     A.total_units = (long long)A.nsx * A.ncy * pairs;
+    A.seam_first = 0;
+    A.signal_units = A.total_units;
+    if (A.done_counter != nullptr && A.ncy >= 2 && A.chunk_rows >= T) {
+        // Rows [0, up_lo) and [dn_hi, H) are ghost rows the neighbours store into; [up_lo, up_hi) and [dn_lo, dn_hi)
+        // are the rows this strip pushes.  Early signalling is safe when only the first and the last chunk touch them.
+        const int first_end = A.out_lo + A.chunk_rows, last_start = A.out_lo + (A.ncy - 1) * A.chunk_rows;
+        const bool top_ok = A.peer_up == nullptr || first_end >= std::max(A.up_hi, A.up_lo + T);
+        const bool bot_ok = A.peer_dn == nullptr || last_start <= std::min(A.dn_lo, A.dn_hi - T);
+        if (top_ok && bot_ok) {
+            A.seam_first = 1;
+            A.signal_units = (long long)A.nsx * 2 * pairs;
+        }
+    }
     if (wpc < 1) wpc = 1;
     if (wpc > 4) wpc = 4;
     while (wpc > 1 && (size_t)wpc * G.smem_per_warp > 227 * 1024) --wpc;

@@ -144,8 +144,10 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     if (unit >= A.total_units) return;
     const int sx = (int)(unit % A.nsx);
     const long long tt = unit / A.nsx;
-    const int cy = (int)(tt % A.ncy);
+    int cy = (int)(tt % A.ncy);
     const int z = (int)(tt / A.ncy);
+    if (PEER && A.seam_first && A.ncy > 2) cy = cy == 0 ? 0 : (cy == 1 ? A.ncy - 1 : cy - 1);   // seam chunks run first
+    const bool counted = !PEER || !A.seam_first || cy == 0 || cy == A.ncy - 1;
     const int W = A.W, H = A.H;
     const int R0 = A.out_lo + cy * A.chunk_rows;
     const int R1 = min(R0 + A.chunk_rows, A.out_hi);
@@ -469,15 +471,16 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         gen_end = last_tick + 1;                                 // bottom edge / remainder: generic ticks
     }
 
-    // Halo-exchange signal: every unit counts itself done after its stores (local and peer) are visible system-wide;
-    // the last one resets the counter and publishes the epoch to both neighbours, whose streams wait on that word
-    // (cuStreamWaitValue32) before they launch the next block.  No kernel ever spins on it.
-    if (PEER && A.done_counter != nullptr) {
+    // Halo-exchange signal: every counted unit (all of them, or just the two seam chunks -- StreamArgs::seam_first)
+    // counts itself done after its stores (local and peer) are visible system-wide; the last one resets the counter
+    // and publishes the epoch to both neighbours, whose streams wait on that word (cuStreamWaitValue32) before they
+    // launch the next block.  No kernel ever spins on it.
+    if (PEER && A.done_counter != nullptr && counted) {
         __syncwarp();
         if (lane == 0) {
             __threadfence_system();
             const unsigned prev = atomicAdd(A.done_counter, 1u);
-            if (prev == (unsigned)(A.total_units - 1)) {
+            if (prev == (unsigned)(A.signal_units - 1)) {
                 *A.done_counter = 0u;
                 __threadfence_system();
                 if (A.flag_up) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.flag_up), "r"(A.epoch) : "memory");

@@ -132,9 +132,21 @@ static void free_planes(hsflow* h) {
     h->prepared = 0;
 }
 
+// temporal_block = 0.  Throughput regime (enough work units for two full waves of resident warps even at the
+// smallest chunk height): the deepest block that still runs without spills.  Latency regime (single frames up to
+// about 4K): a launch is one partly filled wave whose length is (chunk + 2T) x T stage-rows, so a shallower block wins
+// (tools/small_frame_probe.py: 600x480 x 100 iterations 0.31 ms at T = 4 against 0.48 ms at T = 6).  Strips keep the
+// default: every strip of a frame has to issue the same launch sequence.
+static int auto_T(const hsflow* h) {
+    if (h->W <= 0 || h->connected || !h->top_edge || !h->bottom_edge) return kDefaultT;
+    const StreamGeom G = stream_geometry(kDefaultT);
+    const long long nsx = (h->W + G.valid_w - 1) / G.valid_w;
+    const long long units = nsx * ((h->H + 4 * kDefaultT - 1) / (4 * kDefaultT)) * std::max(1, std::min(h->P, h->S));
+    return units >= 2LL * h->sm_count * 8 ? kDefaultT : kSmallT;
+}
 static int effective_T(const hsflow* h) {
     if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1 || h->eps > 0.0) return 1;
-    int T = h->tblock > 0 ? h->tblock : kDefaultT;
+    int T = h->tblock > 0 ? h->tblock : auto_T(h);
     return std::min(T, kMaxT);
 }
 static bool use_stream_kernel(const hsflow* h, int t) {
@@ -461,21 +473,26 @@ static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* 
     return HSFLOW_OK;
 }
 
-// Rows per work unit.  Every unit re-computes 2T warm-up rows, and the launch ends with a partly
-// filled wave of resident warps: pick the chunk height that maximises
-//   chunk/(chunk + 2T)  x  units / (ceil(units/slots) x slots).
+// Rows per work unit.  A unit streams chunk + 2T rows (T warm-up rows above and below; those 2T ticks run in the
+// generic, predicated path at roughly a third of the steady-state speed) plus a fixed prologue worth about 4 rows,
+// and a launch runs ceil(units / resident warps) waves of units one after the other: pick the chunk height that
+// minimises   waves x (chunk + 6T + 4).   With many units this is "least redundant work, fullest last wave"; with
+// few (one small frame) it makes the single wave as short as possible.  Heights are multiples of the TMA box rows
+// so that every chunk enters the steady state without extra generic ticks (1080p, T = 4: 464 us per 100 iterations
+// with 16-row chunks, 544 us with 15).
 static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T, int wpc) {
     if (h->chunk_rows > 0) return std::min(h->chunk_rows, rows);
     const long long slots = (long long)h->sm_count * std::max(1, stream_warps_per_sm(T, h->stencil, wpc));
-    double best = -1.0;
+    long long best = -1;
     int best_ch = rows;
+    const int rg = stream_geometry(T).rows_per_box;
     for (int ncy = 1; ncy <= rows; ++ncy) {
-        const int ch = (rows + ncy - 1) / ncy;
-        if (ch < 4 * T && ncy > 1) break;
+        const int ch = ((rows + ncy - 1) / ncy + rg - 1) / rg * rg;
+        if (ch < 8 && ncy > 1) break;
         const long long units = (long long)nsx * ((rows + ch - 1) / ch) * pairs;
         const long long waves = (units + slots - 1) / slots;
-        const double eff = (double)ch / (ch + 2.0 * T) * (double)units / (double)(waves * slots);
-        if (eff > best + 1e-9) { best = eff; best_ch = ch; }
+        const long long cost = waves * (ch + 6LL * T + 4);
+        if (best < 0 || cost < best) { best = cost; best_ch = ch; }
         if (ncy > 4096) break;
     }
     return best_ch;

@@ -64,16 +64,18 @@ def test_row_strips_over_nccl_bit_identical_to_one_gpu(tmp_path, T, ghost, N):
     assert (u.view(np.uint32) == whole[0].view(np.uint32)).all() and (v.view(np.uint32) == whole[1].view(np.uint32)).all()
 
 
-@pytest.mark.parametrize("T,ghost,N", [(4, 4, 22), (4, 6, 40), (1, 1, 7), (8, 8, 19)])
-def test_row_strips_with_peer_stores_bit_identical_to_one_gpu(tmp_path, T, ghost, N):
+@pytest.mark.parametrize("T,ghost,N,rows", [(4, 4, 22, 64), (4, 6, 40, 64), (1, 1, 7, 64), (8, 8, 19, 64),
+                                            (6, 6, 60, 1024), (0, 6, 45, 700)])
+def test_row_strips_with_peer_stores_bit_identical_to_one_gpu(tmp_path, T, ghost, N, rows):
     """transport="p2p": the iteration kernel pushes the seam rows into the neighbours' buffers over NVLink and
-    signals an epoch word; no exchange step.  Must equal the single-GPU field bit for bit."""
+    signals an epoch word; no exchange step.  Must equal the single-GPU field bit for bit.  The tall cases have
+    many row chunks per strip: the seam chunks run first and the epoch is published while the interior still runs."""
     world = min(_ngpu(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     import torch.multiprocessing as mp
     import opticalflowhs_b200 as P
-    W, H = 1000, 64 * world + 9
+    W, H = (1000 if rows == 64 else 3000), rows * world + 9
     with P.HSFlow(0) as e:
         e.set_params(15.0, N, P.STENCIL_CL8, True, T)
         e.configure(W, H, 1).synth_frames(0, 0, 4321).compute()
