@@ -143,20 +143,42 @@ class NumpyEngine:
             lo = 0 if self.top else t
             hi = self.H if self.bottom else self.H - t
             assert (self.top or self.push[0][0] >= t) and (self.bottom or self.H - self.push[1][1] >= t) and lo < hi
-            u, v = src[0].copy(), src[1].copy()
-            for _ in range(t):
-                u, v = M.sweep_direct(u, v, self.a, self.b, self.c, True)    # rows within t of a seam go stale, unused
+            # Seam-first schedule of the kernel (StreamArgs::seam_first): the row chunks that read ghost rows or push seam
+            # rows are computed and stored first and the epoch goes out right after them; the interior follows LATER
+            # and from a fresh read of the source rows it depends on -- by then a neighbour that ran ahead may already
+            # have stored its next block's seam rows into this source buffer's ghost rows.
+            first_end = lo if self.peer[0] is None else max(self.push[0][1], self.push[0][0] + t)
+            last_start = hi if self.peer[1] is None else min(self.push[1][0], self.push[1][1] - t)
+            seam_first = first_end <= last_start
+
+            def block(r0, r1):                                                # rows [r0, r1) of time step +t from src
+                a0, a1 = max(r0 - t, 0), min(r1 + t, self.H)
+                uu, vv = src[0][a0:a1].copy(), src[1][a0:a1].copy()
+                for _ in range(t):                                            # rows within t of a crop edge go stale, unused
+                    uu, vv = M.sweep_direct(uu, vv, self.a[a0:a1], self.b[a0:a1], self.c[a0:a1], True)
+                return uu[r0 - a0:r1 - a0], vv[r0 - a0:r1 - a0]
+
             self.epoch += 1
-            dst[0][lo:hi], dst[1][lo:hi] = u[lo:hi], v[lo:hi]
-            for d in range(2):                                                # the kernel's second store: seam rows
-                if self.peer[d] is not None:
-                    plo, phi, delta = self.push[d]
-                    pb = self.peer[d][0][self.cur ^ 1]
-                    pb[0][plo + delta:phi + delta] = u[plo:phi]
-                    pb[1][plo + delta:phi + delta] = v[plo:phi]
+            parts = [(lo, first_end), (last_start, hi)] if seam_first else [(lo, hi)]
+            for r0, r1 in parts:
+                if r0 < r1:
+                    uu, vv = block(r0, r1)
+                    dst[0][r0:r1], dst[1][r0:r1] = uu, vv
+                    for d in range(2):                                        # the kernel's second store: seam rows
+                        if self.peer[d] is not None:
+                            plo, phi, delta = self.push[d]
+                            q0, q1 = max(plo, r0), min(phi, r1)
+                            if q0 < q1:
+                                pb = self.peer[d][0][self.cur ^ 1]
+                                pb[0][q0 + delta:q1 + delta] = uu[q0 - r0:q1 - r0]
+                                pb[1][q0 + delta:q1 + delta] = vv[q0 - r0:q1 - r0]
             for d in range(2):                                                # ... then the epoch word
                 if self.peer[d] is not None:
                     self.peer[d][1][1 - d] = self.epoch                      # upper neighbour's word [1], lower's word [0]
+            if seam_first and first_end < last_start:
+                time.sleep(0.002 * (1 + self.epoch % 3))                      # let the neighbours run ahead
+                uu, vv = block(first_end, last_start)
+                dst[0][first_end:last_start], dst[1][first_end:last_start] = uu, vv
             deadline = time.time() + 60
             for d in range(2):                                                # cuStreamWaitValue32(sig[d] >= epoch)
                 while self.peer[d] is not None and self.sig[d] < self.epoch:
