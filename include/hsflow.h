@@ -151,6 +151,18 @@ int hsflow_dot_mask(hsflow_t* h, int pair, int step, float threshold, uint8_t* m
  * u_out/v_out: n_pairs x W*H floats.  Pinned host memory gives full PCIe rate. */
 int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out);
 
+/* ---- frame sequences: replaces the camera loop (cpp:800-842), where every grabbed frame is paired with
+ *      the previous one and then becomes the previous one itself (cpp:834 memcpy I2 -> I1) ---------------
+ * Batch form: frames = n_frames consecutive gray8 images (W*H each); pair k = (frame k, frame k+1), so
+ * u_out/v_out receive n_frames - 1 fields.  Same three-stage pipeline as hsflow_run_batch_host, but a
+ * frame crosses PCIe once and is never copied on the device: the second-frame plane of a sub-batch is its
+ * first-frame plane shifted by one frame. */
+int hsflow_run_sequence_host(hsflow_t* h, const uint8_t* frames, int n_frames, int w, int hgt, float* u_out, float* v_out);
+/* Streaming form for a handle configured with one pair: the current second frame becomes the first
+ * (pointer swap in HBM), `frame` is uploaded as the new second frame; then hsflow_compute as usual.
+ * The very first frame pushed fills both planes (zero flow). */
+int hsflow_push_frame_gray8(hsflow_t* h, const uint8_t* frame, size_t pitch);
+
 /* ---- instrumentation ------------------------------------------------------------------ */
 float hsflow_last_ms(hsflow_t* h, int phase);         /* CUDA-event time of the last call's phase  */
 long long hsflow_kernel_launches(hsflow_t* h);        /* kernels launched by this handle so far    */

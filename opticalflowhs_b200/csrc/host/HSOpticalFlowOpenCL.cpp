@@ -197,12 +197,18 @@ int HSOpticalFlowOpenCL::runFrameSequence() {
     if (setupCL() != SDK_SUCCESS) return SDK_FAILURE;
     uHost.assign((size_t)w * h, 0.f); vHost.assign((size_t)w * h, 0.f);
     double ms = 0;
+    if (hsflow_configure(engine, w, h, 1) != HSFLOW_OK || hsflow_push_frame_gray8(engine, prev.data(), 0) != HSFLOW_OK) {
+        std::cout << "hsflow: " << hsflow_last_error() << std::endl;
+        return SDK_FAILURE;
+    }
     for (int k = 1;; ++k) {
         int w2 = 0, h2 = 0;
         snprintf(path, sizeof path, pattern, k);
         if (loadGray(path, cur, w2, h2) != 0 || w2 != w || h2 != h) break;
         const auto t0 = std::chrono::steady_clock::now();
-        int rc = hsflow_load_pair_gray8(engine, prev.data(), cur.data(), w, h, 0);   // u, v re-zeroed per pair (cpp:331-332)
+        // cpp:834: the previous frame is already in HBM -- it becomes the first frame by a pointer swap, only the new
+        // frame crosses PCIe; u, v are re-zeroed per pair (cpp:331-332)
+        int rc = hsflow_push_frame_gray8(engine, cur.data(), 0);
         if (rc == HSFLOW_OK) rc = hsflow_compute(engine);
         if (rc == HSFLOW_OK) rc = hsflow_read_uv(engine, 0, uHost.data(), vHost.data(), 0);
         ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -443,15 +443,18 @@ int hsflow_load_pair_f32(hsflow_t* h, const float* f1, const float* f2, int w, i
 }
 
 // derivatives of pairs [p0, p0+n) into coefficient slots [0, n)
-static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* o1, float* o2, long long c_rp, long long c_pp) {
+static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* o1, float* o2, long long c_rp, long long c_pp,
+                     const uint8_t* f1base = nullptr, const uint8_t* f2base = nullptr) {
+    if (!f1base) f1base = h->f1;                   // sequence mode passes f2base = f1base + one frame: pair k = frames k, k+1
+    if (!f2base) f2base = h->f2;
     DerivArgs A;
     A.f_row_pitch = h->f_row_pitch; A.f_pair_pitch = h->f_pair_pitch;
     A.c0 = o0; A.c1 = o1; A.c2 = o2;
     A.c_row_pitch = c_rp; A.c_pair_pitch = c_pp;
     A.W = h->W; A.H = h->H; A.normalise = normalise; A.rho = h->rho;
     if (h->deriv == HSFLOW_DERIV_CL) {
-        A.f1 = h->f1 + (size_t)p0 * h->f_pair_pitch;
-        A.f2 = h->f2 + (size_t)p0 * h->f_pair_pitch;
+        A.f1 = f1base + (size_t)p0 * h->f_pair_pitch;
+        A.f2 = f2base + (size_t)p0 * h->f_pair_pitch;
         CK(launch_deriv(A, h->fmt, n, h->stream));
         h->launches++;
     } else {
@@ -464,8 +467,8 @@ static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* 
                 return fail(HSFLOW_ENOMEM, "cudaMalloc of blur planes failed");
             }
         }
-        CK(launch_box3(h->f1 + (size_t)p0 * h->f_pair_pitch, h->fb1, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
-        CK(launch_box3(h->f2 + (size_t)p0 * h->f_pair_pitch, h->fb2, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
+        CK(launch_box3(f1base + (size_t)p0 * h->f_pair_pitch, h->fb1, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
+        CK(launch_box3(f2base + (size_t)p0 * h->f_pair_pitch, h->fb2, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
         A.f1 = h->fb1; A.f2 = h->fb2;
         CK(launch_deriv_cv(A, n, h->stream));
         h->launches += 3;
@@ -648,14 +651,14 @@ int hsflow_iterate(hsflow_t* h, int n) {
 int hsflow_halo_refreshed(hsflow_t* h) { NEED(h); h->valid_lo = 0; h->valid_hi = h->H; return HSFLOW_OK; }
 
 // derivative pass + all iterations for pairs [p0, p0+n) (n <= S); the result lands in the A planes
-static int compute_subbatch(hsflow* h, int p0, int n) {
+static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nullptr, const uint8_t* f2base = nullptr) {
     const int T = effective_T(h), N = h->iterations;
     const bool streamk = use_stream_kernel(h, std::min(T, std::max(N, 1)));
     int L = 0;                                     // ping-pong flips
     for (int left = N; left > 0;) { const int t = std::min(left, T); L += use_stream_kernel(h, t) ? 1 : t; left -= t; }
     (void)streamk;
     const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
-    int rc = run_deriv(h, p0, n, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp);
+    int rc = run_deriv(h, p0, n, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp, f1base, f2base);
     if (rc) return rc;
     h->coef_norm = norm;
     int src = (L % 2 == 0) ? 0 : 1;                // so that the last flip lands in A
@@ -888,20 +891,25 @@ int hsflow_dot_mask(hsflow_t* h, int pair, int step, float thr, uint8_t* mask, i
     return HSFLOW_OK;
 }
 
-int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out) {
-    NEED(h);
+// Three-stage pipeline over sub-batches of B pairs: H2D of sub-batch i+1, compute of i and D2H of i-1 overlap on three
+// streams.  sequence = 0: `frames` holds n_pairs x (f1, f2).  sequence = 1: `frames` holds n_pairs + 1 consecutive
+// frames and pair k = (frame k, frame k+1) -- the camera loop of cpp:800-842, where the second frame of one pair is
+// the first of the next (cpp:834 memcpy I2 -> I1): here each slot holds B + 1 frames in ONE plane and the second-frame
+// pointer is the first-frame pointer plus one frame, so a frame is uploaded once and never copied.
+static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out, int sequence) {
     if (!frames || !u_out || !v_out || n_pairs <= 0) return fail(HSFLOW_EINVAL, "bad argument");
     if (!h->top_edge || !h->bottom_edge) return fail(HSFLOW_EINVAL, "not available in strip mode");
     const long long px = (long long)w * hgt;
     int B = (int)std::max<long long>(1, std::min<long long>(16, (32LL << 20) / std::max<long long>(px, 1)));
     B = std::min(B, n_pairs);
     const int K = 3;                               // sub-batches in flight: H2D | compute | D2H
-    if (!(h->W == w && h->H == hgt && h->P == K * B && h->S == B)) {
+    const int slot_pairs = B + (sequence ? 1 : 0); // frame (and result) slots per sub-batch
+    if (!(h->W == w && h->H == hgt && h->P == K * slot_pairs && h->S == B)) {
         const int keep = h->sub_batch;
         CK(cudaStreamSynchronize(h->stream));
         free_planes(h); h->W = h->H = h->P = 0;
         h->sub_batch = B;
-        int rc = hsflow_configure(h, w, hgt, K * B);
+        int rc = hsflow_configure(h, w, hgt, K * slot_pairs);
         h->sub_batch = keep;
         if (rc) return rc;
     }
@@ -921,17 +929,23 @@ int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w
     const int nsb = (n_pairs + B - 1) / B;
     int status = HSFLOW_OK;
     for (int i = 0; i < nsb && status == HSFLOW_OK; ++i) {
-        const int slot = i % K, p0 = slot * B, first = i * B, n = std::min(B, n_pairs - first);
+        const int slot = i % K, p0 = slot * slot_pairs, first = i * B, n = std::min(B, n_pairs - first);
         if (i >= K) CK(cudaStreamWaitEvent(h->s_in, ev_comp[slot], 0));      // frames of the slot were consumed
-        for (int k = 0; k < n; ++k) {
-            const uint8_t* src = frames + (size_t)(first + k) * 2 * fbytes;
-            CK(cudaMemcpy2DAsync(h->f1 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src, w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
-            CK(cudaMemcpy2DAsync(h->f2 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src + fbytes, w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
+        if (sequence) {
+            for (int k = 0; k <= n; ++k)
+                CK(cudaMemcpy2DAsync(h->f1 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, frames + (size_t)(first + k) * fbytes,
+                                     w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
+        } else {
+            for (int k = 0; k < n; ++k) {
+                const uint8_t* src = frames + (size_t)(first + k) * 2 * fbytes;
+                CK(cudaMemcpy2DAsync(h->f1 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src, w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
+                CK(cudaMemcpy2DAsync(h->f2 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src + fbytes, w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
+            }
         }
         CK(cudaEventRecord(ev_in[slot], h->s_in));
         CK(cudaStreamWaitEvent(h->stream, ev_in[slot], 0));
         if (i >= K) CK(cudaStreamWaitEvent(h->stream, ev_out[slot], 0));     // u/v of the slot were read back
-        status = compute_subbatch(h, p0, n);
+        status = sequence ? compute_subbatch(h, p0, n, h->f1, h->f1 + h->f_pair_pitch) : compute_subbatch(h, p0, n);
         if (status) break;
         CK(cudaEventRecord(ev_comp[slot], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, ev_comp[slot], 0));
@@ -946,6 +960,38 @@ int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w
     h->cur = 0; h->prepared = 0;
     if (status) return status;
     CK(cudaGetLastError());
+    return HSFLOW_OK;
+}
+
+int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out) {
+    NEED(h);
+    return run_pipeline(h, frames, n_pairs, w, hgt, u_out, v_out, 0);
+}
+int hsflow_run_sequence_host(hsflow_t* h, const uint8_t* frames, int n_frames, int w, int hgt, float* u_out, float* v_out) {
+    NEED(h);
+    if (n_frames < 2) return fail(HSFLOW_EINVAL, "a sequence needs at least two frames");
+    return run_pipeline(h, frames, n_frames - 1, w, hgt, u_out, v_out, 1);
+}
+
+// Camera-loop step on the device (cpp:800-842): the second frame of the handle's pair becomes the first one (cpp:834
+// copies I2 over I1; here the two plane pointers swap) and `frame` is uploaded as the new second frame.
+int hsflow_push_frame_gray8(hsflow_t* h, const uint8_t* frame, size_t pitch) {
+    NEED(h);
+    if (!frame) return fail(HSFLOW_EINVAL, "null frame pointer");
+    if (h->P != 1) return fail(HSFLOW_EINVAL, "hsflow_push_frame_gray8 needs a handle configured for one pair");
+    const bool first = h->fmt != FMT_GRAY8 || !h->f1;
+    int rc = ensure_frames(h, FMT_GRAY8);
+    if (rc) return rc;
+    const size_t wbytes = (size_t)h->W;
+    if (pitch == 0) pitch = wbytes;
+    if (pitch < wbytes) return fail(HSFLOW_EINVAL, "pitch %zu smaller than a row (%zu bytes)", pitch, wbytes);
+    phase_begin(h, HSFLOW_PHASE_LOAD);
+    std::swap(h->f1, h->f2);
+    CK(cudaMemcpy2DAsync(h->f2, h->f_row_pitch, frame, pitch, wbytes, h->H, cudaMemcpyHostToDevice, h->stream));
+    if (first)                                     // very first frame: both planes hold it (zero flow until the next push)
+        CK(cudaMemcpy2DAsync(h->f1, h->f_row_pitch, frame, pitch, wbytes, h->H, cudaMemcpyHostToDevice, h->stream));
+    phase_end(h, HSFLOW_PHASE_LOAD);
+    h->prepared = 0;
     return HSFLOW_OK;
 }
 

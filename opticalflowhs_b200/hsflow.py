@@ -68,6 +68,8 @@ SIGNATURES = {
     "hsflow_get_device_frames": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "hsflow_dot_mask": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, _P, C.POINTER(C.c_int)]),
     "hsflow_run_batch_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "hsflow_run_sequence_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "hsflow_push_frame_gray8": (C.c_int, [_P, _P, C.c_size_t]),
     "hsflow_last_ms": (C.c_float, [_P, C.c_int]),
     "hsflow_kernel_launches": (C.c_longlong, [_P]),
     "hsflow_iterations_done": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
@@ -276,6 +278,20 @@ class HSFlow:
         self._ck(self._L.hsflow_run_batch_host(self._h, _ptr(frames), n, W, H, _ptr(u_out), _ptr(v_out)))
         self.W, self.H = W, H
         return self
+
+    def run_sequence_host(self, frames, u_out, v_out):
+        """frames: uint8 (n+1,H,W) consecutive frames; pair k = (frame k, frame k+1); u_out/v_out: float32 (n,H,W)."""
+        n1, H, W = frames.shape
+        assert n1 >= 2 and u_out.shape == (n1 - 1, H, W) and v_out.shape == (n1 - 1, H, W)
+        self._ck(self._L.hsflow_run_sequence_host(self._h, _ptr(frames), n1, W, H, _ptr(u_out), _ptr(v_out)))
+        self.W, self.H = W, H
+        return self
+
+    def push_frame(self, frame):
+        """Camera-loop step: the second frame becomes the first, `frame` (uint8 (H,W)) the new second one."""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        assert frame.shape == (self.H, self.W)
+        self._ck(self._L.hsflow_push_frame_gray8(self._h, _ptr(frame), 0)); return self
 
     # ---- instrumentation
     def last_ms(self, phase):

@@ -272,6 +272,39 @@ def test_pipelined_host_batch_equals_per_pair_compute(P, oracle):
 
 # ---- strips: host-mediated halo exchange on one GPU ---------------------------------------------------
 
+def test_frame_sequence_pipeline_and_push_frame_equal_per_pair_compute(P, oracle):
+    """hsflow_run_sequence_host (pair k = frames k, k+1; one upload per frame) and the streaming hsflow_push_frame_gray8
+    loop (cpp:800-842 with the cpp:834 frame hand-over as a pointer swap) against loading every pair separately."""
+    from opticalflowhs_b200.hsflow import pinned_empty
+    W, H, n = 232, 100, 37                               # 38 frames -> 37 pairs: several sub-batches, a ragged last one
+    frames = pinned_empty((n + 1, H, W), np.uint8)
+    for k in range(n + 1):
+        frames[k] = oracle.synth_pair(W, H, seed=500 + k)[k & 1]
+    uo, vo = pinned_empty((n, H, W), np.float32), pinned_empty((n, H, W), np.float32)
+    want = []
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, 17, P.STENCIL_CL8, True, 4)
+        for k in range(n):
+            e.load_pair(frames[k], frames[k + 1]).compute()
+            want.append(e.read_uv())
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, 17, P.STENCIL_CL8, True, 4)
+        e.run_sequence_host(frames, uo, vo)
+        for k in range(n):
+            assert (bits(uo[k]) == bits(want[k][0])).all() and (bits(vo[k]) == bits(want[k][1])).all(), k
+        e.run_sequence_host(frames[:2], uo[:1], vo[:1])  # shortest sequence, re-configures the handle
+        assert (bits(uo[0]) == bits(want[0][0])).all()
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, 17, P.STENCIL_CL8, True, 4).configure(W, H, 1)
+        e.push_frame(frames[0]).compute()
+        u, v = e.read_uv()
+        assert not u.any() and not v.any()              # a single frame: both planes equal, zero flow
+        for k in range(6):
+            e.push_frame(frames[k + 1]).compute()
+            u, v = e.read_uv()
+            assert (bits(u) == bits(want[k][0])).all() and (bits(v) == bits(want[k][1])).all(), k
+
+
 @pytest.mark.parametrize("T,ghost", [(1, 1), (4, 4), (4, 8), (3, 6)])
 def test_row_strips_with_halo_exchange_equal_whole_frame(P, oracle, T, ghost):
     W, H, N, nstrips = 180, 90, 2 * ghost + 3, 3
@@ -417,6 +450,29 @@ def test_full_size_frame_windows_against_oracle_crops(P, oracle, W, H, N, T):
         x0, x1 = max(x - N, 0), min(x + K + N, W)
         uo, vo = oracle.run_cl(f1[y0:y1, x0:x1], f2[y0:y1, x0:x1], 15.0, N, True)
         # the derivative tap j+1/i+1 and N sweeps stay inside the crop except at true image edges
+        yy, xx = y - y0, x - x0
+        du = np.abs(u[y:y + K, x:x + K] - uo[yy:yy + K, xx:xx + K]).max()
+        dv = np.abs(v[y:y + K, x:x + K] - vo[yy:yy + K, xx:xx + K]).max()
+        assert du <= TOL_MAX and dv <= TOL_MAX, (y, x, du, dv)
+
+
+def test_16k_frame_500_iterations_windows_against_oracle_crops(P, oracle):
+    """BASELINE.json configs[4] at full size on one GPU (auto temporal block): windows on strip and chunk seams, at the
+    image corners and in the middle, each checked against the oracle on its domain of dependence."""
+    W = H = 16384
+    N, K = 500, 40
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 0)
+        e.configure(W, H, 1).synth_frames(0, 0, 1234).compute()
+        assert e.temporal_block == 6
+        u, v = e.read_uv()
+    assert np.isfinite(u[::7, ::5]).all() and np.isfinite(v[::7, ::5]).all()
+    spots = [(0, 0), (H - K, W - K), (2049 - K // 2, 73 * 112 - K // 2), (H // 2 + 3, W // 3)]
+    for (y, x) in spots:
+        y0, y1 = max(y - N, 0), min(y + K + N, H)
+        x0, x1 = max(x - N, 0), min(x + K + N, W)
+        f1, f2 = oracle.synth_pair(W, H, seed=1234, row0=y0, rows=y1 - y0)
+        uo, vo = oracle.run_cl(np.ascontiguousarray(f1[:, x0:x1]), np.ascontiguousarray(f2[:, x0:x1]), 15.0, N, True)
         yy, xx = y - y0, x - x0
         du = np.abs(u[y:y + K, x:x + K] - uo[yy:yy + K, xx:xx + K]).max()
         dv = np.abs(v[y:y + K, x:x + K] - vo[yy:yy + K, xx:xx + K]).max()
