@@ -74,7 +74,8 @@ int hsflow_set_params(hsflow_t* h, float alpha, int iterations, int stencil, int
 int hsflow_set_lambda(hsflow_t* h, float lambda);         /* rho = 1/lambda (cv.cpp:29)          */
 int hsflow_set_math(hsflow_t* h, int math_mode);          /* HSFLOW_MATH_*                      */
 int hsflow_set_deriv(hsflow_t* h, int deriv_mode);        /* HSFLOW_DERIV_*                     */
-int hsflow_set_tuning(hsflow_t* h, int chunk_rows, int warps_per_cta, int sub_batch); /* 0 = auto */
+/* 0 = auto.  warps_per_cta is accepted and ignored: the streaming kernel always runs one autonomous warp per CTA. */
+int hsflow_set_tuning(hsflow_t* h, int chunk_rows, int warps_per_cta, int sub_batch);
 int hsflow_set_warm_start(hsflow_t* h, int keep_uv);      /* use_previous (cv.h:481-483)        */
 /* The EPS half of cvTermCriteria(CV_TERMCRIT_ITER | CV_TERMCRIT_EPS, it, 1e-6) (OpticalFlowOpenCV.cpp:29,
  * 94): every pair stops after the first sweep whose max |new - old| over u and v is < eps, or after

@@ -101,10 +101,10 @@ constexpr int kDefaultT = 6;           // temporal_block = 0: fastest sustained 
 constexpr int kSmallT = 4;             // ... when the job cannot fill the GPU twice over: shorter warm-up, shorter units
 StreamGeom stream_geometry(int T);
 cudaError_t stream_prepare(int device);     // opt in to large dynamic shared memory for every instantiation
-int stream_warps_per_sm(int T, int stencil, int warps_per_cta);   // resident warps per SM (occupancy API)
+int stream_warps_per_sm(int T, int stencil);   // resident warps (= CTAs) per SM (occupancy API)
 // maps: row-interleaved u/v source {W,2,H,pairs} and coefficients {W,3,H,pairs}, box = 128 columns x all planes x
-// stream_geometry(T).rows_per_box rows.  warps_per_cta in 1..4.
+// stream_geometry(T).rows_per_box rows.  One warp per CTA.
 cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tm_uv, const CUtensorMap& tm_c,
-                                 StreamArgs A, int pairs, int warps_per_cta, cudaStream_t s);
+                                 StreamArgs A, int pairs, cudaStream_t s);
 
 }  // namespace hs

@@ -8,8 +8,8 @@ namespace hs {
 
 #define HS_DECL(k)                                                                                                     \
     cudaError_t stream_prep_T##k();                                                                                    \
-    cudaError_t stream_launch_T##k(int, bool, const CUtensorMap&, const CUtensorMap&, const StreamArgs&, int, cudaStream_t); \
-    int stream_occ_T##k(int, int);
+    cudaError_t stream_launch_T##k(int, bool, const CUtensorMap&, const CUtensorMap&, const StreamArgs&, cudaStream_t); \
+    int stream_occ_T##k(int);
 HS_DECL(1) HS_DECL(2) HS_DECL(3) HS_DECL(4) HS_DECL(5) HS_DECL(6) HS_DECL(7) HS_DECL(8)
 #undef HS_DECL
 
@@ -36,17 +36,17 @@ cudaError_t stream_prepare(int) {
     return stream_prep_T8();
 }
 
-int stream_warps_per_sm(int T, int stencil, int wpc) {
+int stream_warps_per_sm(int T, int stencil) {
     switch (T) {
-        case 1: return stream_occ_T1(stencil, wpc); case 2: return stream_occ_T2(stencil, wpc);
-        case 3: return stream_occ_T3(stencil, wpc); case 4: return stream_occ_T4(stencil, wpc);
-        case 5: return stream_occ_T5(stencil, wpc); case 6: return stream_occ_T6(stencil, wpc);
-        case 7: return stream_occ_T7(stencil, wpc); default: return stream_occ_T8(stencil, wpc);
+        case 1: return stream_occ_T1(stencil); case 2: return stream_occ_T2(stencil);
+        case 3: return stream_occ_T3(stencil); case 4: return stream_occ_T4(stencil);
+        case 5: return stream_occ_T5(stencil); case 6: return stream_occ_T6(stencil);
+        case 7: return stream_occ_T7(stencil); default: return stream_occ_T8(stencil);
     }
 }
 
 cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tuv, const CUtensorMap& tc, StreamArgs A, int pairs,
-                                 int wpc, cudaStream_t s) {
+                                 cudaStream_t s) {
     const StreamGeom G = stream_geometry(T);
     const int rows = A.out_hi - A.out_lo;
     if (rows <= 0 || pairs <= 0) return cudaSuccess;
@@ -66,19 +66,16 @@ cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tuv, con
             A.signal_units = (long long)A.nsx * 2 * pairs;
         }
     }
-    if (wpc < 1) wpc = 1;
-    if (wpc > 4) wpc = 4;
-    while (wpc > 1 && (size_t)wpc * G.smem_per_warp > 227 * 1024) --wpc;
     const bool peer = A.done_counter != nullptr;    // strip connected to its neighbours (hsflow_strip_connect)
     switch (T) {
-        case 1: return stream_launch_T1(stencil, peer, tuv, tc, A, wpc, s);
-        case 2: return stream_launch_T2(stencil, peer, tuv, tc, A, wpc, s);
-        case 3: return stream_launch_T3(stencil, peer, tuv, tc, A, wpc, s);
-        case 4: return stream_launch_T4(stencil, peer, tuv, tc, A, wpc, s);
-        case 5: return stream_launch_T5(stencil, peer, tuv, tc, A, wpc, s);
-        case 6: return stream_launch_T6(stencil, peer, tuv, tc, A, wpc, s);
-        case 7: return stream_launch_T7(stencil, peer, tuv, tc, A, wpc, s);
-        case 8: return stream_launch_T8(stencil, peer, tuv, tc, A, wpc, s);
+        case 1: return stream_launch_T1(stencil, peer, tuv, tc, A, s);
+        case 2: return stream_launch_T2(stencil, peer, tuv, tc, A, s);
+        case 3: return stream_launch_T3(stencil, peer, tuv, tc, A, s);
+        case 4: return stream_launch_T4(stencil, peer, tuv, tc, A, s);
+        case 5: return stream_launch_T5(stencil, peer, tuv, tc, A, s);
+        case 6: return stream_launch_T6(stencil, peer, tuv, tc, A, s);
+        case 7: return stream_launch_T7(stencil, peer, tuv, tc, A, s);
+        case 8: return stream_launch_T8(stencil, peer, tuv, tc, A, s);
         default: return cudaErrorInvalidValue;
     }
 }

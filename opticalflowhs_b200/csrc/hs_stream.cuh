@@ -6,7 +6,7 @@
 //
 // Design (B200-first, HBM-bound fp32 stencil -- no tensor cores on purpose):
 //  * work unit = one WARP x (128-column strip, row chunk, frame pair).  Warps are autonomous:
-//    own shared-memory rings, own mbarriers, no __syncthreads anywhere; one warp per CTA by default.
+//    own shared-memory rings, own mbarriers, no __syncthreads anywhere; one warp per CTA.
 //  * the fp32 planes are row-interleaved in HBM ([row][u|v][pitch], [row][a|b|c][pitch]), so ONE TMA
 //    operation (cp.async.bulk.tensor.4d, box = 128 columns x all planes x 2 rows, issued by one
 //    elected lane) refills a ring slot.  Out-of-image columns are zero-filled by the TMA unit and
@@ -129,7 +129,7 @@ template <int T> struct DefaultCfg {
 #define HS_STREAM_MIN_CTAS 1     // experiments: 3 caps the kernel at 168 registers (12 warps per SM)
 #endif
 template <int T, int ST, bool PEER>
-__global__ void __launch_bounds__(128, HS_STREAM_MIN_CTAS)
+__global__ void __launch_bounds__(32, HS_STREAM_MIN_CTAS)
 k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant__ CUtensorMap tm_c, const StreamArgs A) {
     using C = typename DefaultCfg<T>::type;
     constexpr int RG = C::RG, NGC = C::NGC, NGUV = C::NGUV, DRET = C::DRET;
@@ -139,8 +139,12 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     constexpr int CB = NRC * CROW, UB = NRUV * UROW;        // ring sizes in bytes
     extern __shared__ __align__(128) uint8_t smem_raw[];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long unit = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    // One warp per CTA, always: the unit index is then a function of blockIdx alone, so the whole geometry (strip,
+    // chunk, pair, row range, TMA coordinates, ring phases) is warp-uniform BY CONSTRUCTION and the compiler keeps it
+    // in uniform registers -- with warps sharing a CTA it cannot prove that, and the bookkeeping competes with the
+    // pipeline state for vector registers (T = 6: 255 registers with spills -> 247 without, 10 % fewer instructions).
+    const int lane = threadIdx.x;
+    const long long unit = blockIdx.x;
     if (unit >= A.total_units) return;
     const int sx = (int)(unit % A.nsx);
     const long long tt = unit / A.nsx;
@@ -168,8 +172,8 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     const bool edge = (sx == 0) || (x0 + kStripW - 1 >= W - 1);
     const bool wmis = (W & 3) != 0;
 
-    uint8_t* wsm = smem_raw + (size_t)warp * C::SMEM_WARP;
-    // byte layout per warp: coefficient ring | u/v ring | mbarriers
+    uint8_t* wsm = smem_raw;
+    // byte layout: coefficient ring | u/v ring | mbarriers
     const uint8_t* sa_l = wsm + lane * 16;                  // this lane's 16-byte column group
     const uint8_t* su_l = wsm + CB + lane * 16;
     const uint32_t sa32 = smem_u32(wsm), su32 = sa32 + CB;

@@ -26,29 +26,27 @@ cudaError_t HS_FN(stream_prep_T)() {
 }
 
 template <int ST, bool PEER>
-static cudaError_t launch_one(const CUtensorMap& tuv, const CUtensorMap& tc, const StreamArgs& A, int wpc, cudaStream_t s) {
+static cudaError_t launch_one(const CUtensorMap& tuv, const CUtensorMap& tc, const StreamArgs& A, cudaStream_t s) {
     using C = typename DefaultCfg<kT>::type;
-    const size_t smem = (size_t)wpc * C::SMEM_WARP;
-    const long long ctas = (A.total_units + wpc - 1) / wpc;
+    const long long ctas = A.total_units;              // one autonomous warp per CTA
     if (ctas <= 0) return cudaSuccess;
-    if (ctas > 0x7fffffffLL || smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    k_jacobi_stream<kT, ST, PEER><<<(unsigned)ctas, wpc * 32, smem, s>>>(tuv, tc, A);
+    if (ctas > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    k_jacobi_stream<kT, ST, PEER><<<(unsigned)ctas, 32, C::SMEM_WARP, s>>>(tuv, tc, A);
     return cudaGetLastError();
 }
-cudaError_t HS_FN(stream_launch_T)(int st, bool peer, const CUtensorMap& tuv, const CUtensorMap& tc, const StreamArgs& A, int wpc,
+cudaError_t HS_FN(stream_launch_T)(int st, bool peer, const CUtensorMap& tuv, const CUtensorMap& tc, const StreamArgs& A,
                                    cudaStream_t s) {
-    if (st == ST_CL8) return peer ? launch_one<ST_CL8, true>(tuv, tc, A, wpc, s) : launch_one<ST_CL8, false>(tuv, tc, A, wpc, s);
-    return peer ? launch_one<ST_CV4, true>(tuv, tc, A, wpc, s) : launch_one<ST_CV4, false>(tuv, tc, A, wpc, s);
+    if (st == ST_CL8) return peer ? launch_one<ST_CL8, true>(tuv, tc, A, s) : launch_one<ST_CL8, false>(tuv, tc, A, s);
+    return peer ? launch_one<ST_CV4, true>(tuv, tc, A, s) : launch_one<ST_CV4, false>(tuv, tc, A, s);
 }
 
-int HS_FN(stream_occ_T)(int st, int wpc) {
+int HS_FN(stream_occ_T)(int st) {
     using C = typename DefaultCfg<kT>::type;
     int n = 0;
-    const size_t smem = (size_t)wpc * C::SMEM_WARP;
-    cudaError_t e = st == ST_CL8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_jacobi_stream<kT, ST_CL8, false>, wpc * 32, smem)
-                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_jacobi_stream<kT, ST_CV4, false>, wpc * 32, smem);
+    cudaError_t e = st == ST_CL8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_jacobi_stream<kT, ST_CL8, false>, 32, C::SMEM_WARP)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_jacobi_stream<kT, ST_CV4, false>, 32, C::SMEM_WARP);
     if (e != cudaSuccess) { cudaGetLastError(); return 8; }
-    return n * wpc;
+    return n;
 }
 
 }  // namespace hs

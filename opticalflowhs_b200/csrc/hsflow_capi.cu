@@ -483,9 +483,9 @@ static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* 
 // few (one small frame) it makes the single wave as short as possible.  Heights are multiples of the TMA box rows
 // so that every chunk enters the steady state without extra generic ticks (1080p, T = 4: 464 us per 100 iterations
 // with 16-row chunks, 544 us with 15).
-static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T, int wpc) {
+static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T) {
     if (h->chunk_rows > 0) return std::min(h->chunk_rows, rows);
-    const long long slots = (long long)h->sm_count * std::max(1, stream_warps_per_sm(T, h->stencil, wpc));
+    const long long slots = (long long)h->sm_count * std::max(1, stream_warps_per_sm(T, h->stencil));
     long long best = -1;
     int best_ch = rows;
     const int rg = stream_geometry(T).rows_per_box;
@@ -515,8 +515,7 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         const int nsx = (h->W + G.valid_w - 1) / G.valid_w;
         A.z_in0 = src == 0 ? pA : 0;
         A.z_c0 = 0;
-        const int wpc = h->wpc > 0 ? std::min(h->wpc, 4) : 1;
-        A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, nsx, n, t, wpc);
+        A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, nsx, n, t);
         if (h->connected) {                        // fused halo exchange: seam rows go straight into the neighbours' buffers
             const int dst = src == 0 ? 1 : 0;      // 0 = A planes, 1 = B planes; every strip flips in step
             A.peer_up = h->has_peer[0] ? (float*)h->peer[0][dst] : nullptr;
@@ -530,7 +529,7 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         }
         const int m = G.rows_per_box - 2;
         if (m < 0 || m > 2) return fail(HSFLOW_EINVAL, "internal: no tensor map for %d-row boxes", G.rows_per_box);
-        CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uvA[m] : h->tm_uvB[m], h->tm_c[m], A, n, wpc, h->stream));
+        CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uvA[m] : h->tm_uvB[m], h->tm_c[m], A, n, h->stream));
         h->launches++;
         return HSFLOW_OK;
     }
