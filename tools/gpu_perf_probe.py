@@ -1,4 +1,4 @@
-"""GPU perf probe (not a test): sweeps temporal block / chunk rows / warps per CTA on synthetic frames."""
+"""GPU perf probe (not a test): sweeps temporal block / chunk rows on synthetic frames."""
 import sys, os, time, itertools
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opticalflowhs_b200 as P
@@ -7,9 +7,8 @@ W, H, NP = int(os.environ.get("W", 3840)), int(os.environ.get("H", 2160)), int(o
 N = int(os.environ.get("N", 48))
 configs = []
 for T in (1, 2, 3, 4, 5, 6, 8):
-    for wpc in (4, 8):
-        for chunk in (0, 64, 128, 270):
-            configs.append((2, T, wpc, chunk))
+    for chunk in (0, 64, 128, 270):
+        configs.append((2, T, 0, chunk))
 configs = [(1, 1, 0, 0), (1, 1, 0, 32), (1, 1, 0, 256)] + configs
 sel = os.environ.get("SEL")
 e = P.HSFlow(0)
