@@ -109,13 +109,25 @@ template <int T, int RG_, int NGC_, int NGUV_> struct StreamCfg {
 // the 227 KB of an SM, and the unrolled trip has to stay inside the 32 KB instruction cache:
 //   T <= 3: 2 rows (occupancy of the shallow blocks)      T = 4: 4 rows (12 + 8 ring rows, 26 KB)
 //   T = 5, 6: 3 rows (12 + 6 ring rows, 24 KB)            T = 7, 8: 2 rows (12 + 4 ring rows, 22 KB)
-// HS_STREAM_RG="{2,2,2,2,4,3,3,2,2}" (index = T) overrides the table for experiments.
-#ifndef HS_STREAM_RG
-#define HS_STREAM_RG {2, 2, 2, 2, 4, 3, 3, 2, 2}
+// -DHS_STREAM_RG_T<k>=<rows> overrides one entry for experiments.
+#ifndef HS_STREAM_RG_T4
+#define HS_STREAM_RG_T4 4
+#endif
+#ifndef HS_STREAM_RG_T5
+#define HS_STREAM_RG_T5 3
+#endif
+#ifndef HS_STREAM_RG_T6
+#define HS_STREAM_RG_T6 3
+#endif
+#ifndef HS_STREAM_RG_T7
+#define HS_STREAM_RG_T7 2
+#endif
+#ifndef HS_STREAM_RG_T8
+#define HS_STREAM_RG_T8 2
 #endif
 constexpr int stream_rows_per_box(int T) {
-    constexpr int tab[9] = HS_STREAM_RG;
-    return tab[T];
+    return T == 4 ? HS_STREAM_RG_T4 : T == 5 ? HS_STREAM_RG_T5 : T == 6 ? HS_STREAM_RG_T6 : T == 7 ? HS_STREAM_RG_T7
+         : T == 8 ? HS_STREAM_RG_T8 : 2;
 }
 template <int T> struct DefaultCfg {
     static constexpr int RG = stream_rows_per_box(T);
