@@ -151,7 +151,8 @@ static int effective_T(const hsflow* h) {
 }
 static bool use_stream_kernel(const hsflow* h, int t) {
     if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1 || h->eps > 0.0) return false;
-    return t >= 2 || h->kernel_sel == 2 || h->connected;   // the peer transport lives in the streaming kernel
+    (void)t;                                       // also for a single iteration: at T = 1 the TMA-fed streaming kernel
+    return true;                                   // moves 5.3 TB/s where k_jacobi1 moves 4.6-4.8 (tools/gpu_perf_probe.py)
 }
 
 // 4-D map {W, planes, H, pairs} over a row-interleaved buffer; box = 128 columns x all planes x box_rows rows
@@ -543,7 +544,17 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
     A.row_pitch = h->uv_rp; A.in_pair_pitch = A.out_pair_pitch = h->uv_pp;
     A.c_row_pitch = h->c_rp; A.c_pair_pitch = h->c_pp;
     A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
-    A.chunk_rows = h->chunk_rows > 0 ? h->chunk_rows : std::max(1, std::min(out_hi - out_lo, 64));
+    if (h->chunk_rows > 0) A.chunk_rows = h->chunk_rows;
+    else {
+        // 64-row chunks re-read 2 halo rows per 64 (3 %).  A single frame cannot fill the GPU that way (1080p: 4 x 17
+        // CTAs): shrink the chunk until there are about eight waves of seven 4-warp CTAs per SM, but not below 8 rows
+        // (25 % re-reads, absorbed by L2) -- or 4 rows when even 8-row chunks leave SMs idle.  100 sweeps with 64-row
+        // chunks / with this rule: 600x480 5.9 / 0.8 ms, 1080p 6.9 / 1.4 ms (tools/small_frame_probe.py).
+        const long long rows = out_hi - out_lo, nx = (h->W + 511) / 512;
+        const long long fit = rows * nx * n / ((long long)h->sm_count * 56);
+        const long long lo = nx * ((rows + 7) / 8) * n < 2LL * h->sm_count ? 4 : 8;
+        A.chunk_rows = (int)std::max<long long>(1, std::min<long long>(rows, std::max<long long>(lo, std::min<long long>(64, fit))));
+    }
     A.rho = h->rho;
     if (h->ec_on) {                                // EPS mode: track max |new - old|, carry converged pairs over
         A.emax = h->d_emax + h->ec_off; A.stop = h->d_stop + h->ec_off;
