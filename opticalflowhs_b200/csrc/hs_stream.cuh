@@ -90,7 +90,10 @@ template <int OFF> __device__ __forceinline__ float4 lds128(uint32_t base) {
 // ---- geometry ------------------------------------------------------------------------------------
 template <int T, int RG_, int NGC_, int NGUV_> struct StreamCfg {
     static constexpr int RG = RG_, NGC = NGC_, NGUV = NGUV_;
-    static constexpr int HL = (T + 3) / 4 * 4;              // column halo per side, multiple of 4
+    // Column halo per side, a multiple of 4: the strip origin x0 = sx * VALIDW - HL is the innermost coordinate of
+    // every TMA box, and the unit faults (the mbarrier never completes) unless that is 16-byte aligned -- a halo of
+    // 6 for T = 5, 6 (34 instead of 35 strips on a 3840-wide frame) was tried and traps.
+    static constexpr int HL = (T + 3) / 4 * 4;
     static constexpr int VALIDW = kStripW - 2 * HL;         // columns a strip produces
     static constexpr int NRC = NGC * RG;                    // coefficient ring rows
     static constexpr int NRUV = NGUV * RG;                  // u/v ring rows
