@@ -926,12 +926,12 @@ static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, in
     int rc = ensure_frames(h, FMT_GRAY8);
     if (rc) return rc;
     if (!h->s_in) { CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)); }
-    cudaEvent_t ev_in[K], ev_comp[K], ev_out[K];
-    for (int k = 0; k < K; ++k) {
-        CK(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_comp[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
-    }
+    struct Events {                                // destroyed on every exit path, error returns included
+        cudaEvent_t e[3 * K] = {};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    cudaEvent_t *ev_in = evs.e, *ev_comp = evs.e + K, *ev_out = evs.e + 2 * K;
+    for (int k = 0; k < 3 * K; ++k) CK(cudaEventCreateWithFlags(&evs.e[k], cudaEventDisableTiming));
     // order the side streams after whatever the handle's stream did so far (allocation memsets)
     CK(cudaEventRecord(ev_comp[0], h->stream));
     CK(cudaStreamWaitEvent(h->s_in, ev_comp[0], 0));
@@ -966,7 +966,6 @@ static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, in
         CK(cudaEventRecord(ev_out[slot], h->s_out));
     }
     cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->s_out);
-    for (int k = 0; k < K; ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_comp[k]); cudaEventDestroy(ev_out[k]); }
     h->cur = 0; h->prepared = 0;
     if (status) return status;
     CK(cudaGetLastError());
