@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include <unistd.h>
 
@@ -109,6 +110,12 @@ struct hsflow {
     int eps_cap = 0;                               // pairs the two arrays hold
     int sweeps = 0;                                // sweeps since hsflow_prepare (hsflow_iterate path)
     int ec_on = 0, ec_sweep = 0, ec_total = 0, ec_off = 0;   // tracking context of the sweep run_block launches next
+    // host pipeline: the last launch of a sub-batch stores PLANAR, densely packed fields ([pair][H][W] of u, then of v)
+    // into a staging slot, so that the read-back is two contiguous copies (56.9 GB/s over PCIe against 51.8 GB/s for
+    // the row-by-row de-interleaving 2-D copy out of the u|v buffer, tools/microbench/d2h_bench.cu)
+    float* stage = nullptr;
+    size_t stage_bytes = 0;
+    float *ov_u = nullptr, *ov_v = nullptr;        // output override of the launch run_block issues next
 };
 
 static void strip_disconnect(hsflow* h) {
@@ -126,6 +133,7 @@ static void free_planes(hsflow* h) {
     if (h->connected) strip_disconnect(h);         // the neighbours' mappings of OUR buffers die with the buffers: reconnect
     cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2);
     cudaFree(h->uA); cudaFree(h->uB); cudaFree(h->c0); cudaFree(h->dtmp);   // vA, vB, c1, c2 point into these
+    cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0;
     h->f1 = h->f2 = h->fb1 = h->fb2 = nullptr;
     h->uA = h->vA = h->uB = h->vB = h->c0 = h->c1 = h->c2 = h->dtmp = nullptr;
     h->fmt = -1;
@@ -511,6 +519,10 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         memset(&A, 0, sizeof A);
         A.u_out = uo; A.v_out = vo;
         A.row_pitch = h->uv_rp; A.out_pair_pitch = h->uv_pp;
+        if (h->ov_u) {                             // planar, dense output (host pipeline, last launch of a sub-batch)
+            A.u_out = h->ov_u; A.v_out = h->ov_v;
+            A.row_pitch = h->W; A.out_pair_pitch = (long long)h->W * h->H;
+        }
         A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
         const StreamGeom G = stream_geometry(t);
         const int nsx = (h->W + G.valid_w - 1) / G.valid_w;
@@ -661,7 +673,10 @@ int hsflow_iterate(hsflow_t* h, int n) {
 int hsflow_halo_refreshed(hsflow_t* h) { NEED(h); h->valid_lo = 0; h->valid_hi = h->H; return HSFLOW_OK; }
 
 // derivative pass + all iterations for pairs [p0, p0+n) (n <= S); the result lands in the A planes
-static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nullptr, const uint8_t* f2base = nullptr) {
+// fin_u / fin_v: where the final fields go instead of the A planes (planar [n][H][W]; needs the streaming kernel for the
+// last block and W % 4 == 0, checked by the caller)
+static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nullptr, const uint8_t* f2base = nullptr,
+                            float* fin_u = nullptr, float* fin_v = nullptr) {
     const int T = effective_T(h), N = h->iterations;
     const bool streamk = use_stream_kernel(h, std::min(T, std::max(N, 1)));
     int L = 0;                                     // ping-pong flips
@@ -679,7 +694,9 @@ static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nu
     for (int left = N; left > 0;) {
         const int t = std::min(left, T);
         if (use_stream_kernel(h, t)) {
+            if (left == t) { h->ov_u = fin_u; h->ov_v = fin_v; }
             rc = run_block(h, t, src, p0, n, 0, h->H);
+            h->ov_u = h->ov_v = nullptr;
             if (rc) return rc;
             src ^= 1;
         } else {
@@ -926,6 +943,17 @@ static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, in
     int rc = ensure_frames(h, FMT_GRAY8);
     if (rc) return rc;
     if (!h->s_in) { CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)); }
+    // planar staging slots for the read-back: possible when the last block of a sub-batch runs in the streaming kernel
+    // (its output addressing is free) and rows of W floats keep the float4 stores aligned
+    const int T_last = h->iterations > 0 ? (h->iterations % effective_T(h) ? h->iterations % effective_T(h) : effective_T(h)) : 0;
+    const bool planar = (w % 4 == 0) && h->iterations > 0 && use_stream_kernel(h, T_last);
+    const size_t slot_floats = 2 * (size_t)B * px;
+    if (planar && h->stage_bytes < K * slot_floats * sizeof(float)) {
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0;
+        if (cudaMalloc(&h->stage, K * slot_floats * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return fail(HSFLOW_ENOMEM, "cudaMalloc of the read-back staging slots failed"); }
+        h->stage_bytes = K * slot_floats * sizeof(float);
+    }
     struct Events {                                // destroyed on every exit path, error returns included
         cudaEvent_t e[3 * K] = {};
         ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
@@ -936,10 +964,23 @@ static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, in
     CK(cudaEventRecord(ev_comp[0], h->stream));
     CK(cudaStreamWaitEvent(h->s_in, ev_comp[0], 0));
     const size_t fbytes = (size_t)px, wb = (size_t)w * sizeof(float);
-    const int nsb = (n_pairs + B - 1) / B;
-    int status = HSFLOW_OK;
-    for (int i = 0; i < nsb && status == HSFLOW_OK; ++i) {
-        const int slot = i % K, p0 = slot * slot_pairs, first = i * B, n = std::min(B, n_pairs - first);
+    // Sub-batch sizes ramp up from one pair and down to one pair again: the read-back is the bottleneck (u, v are 8
+    // bytes per pixel against 2 bytes of frames), so what the call adds to "all results over PCIe" is the time before
+    // the first result can leave (upload + compute of the FIRST sub-batch) and the read-back of the LAST one.
+    std::vector<int> sizes;
+    {
+        std::vector<int> head, tail;
+        int left = n_pairs;
+        for (int s = 1; s < B && left > 2 * B; s *= 2) {           // 1, 2, 4, ... at both ends while there is enough work
+            head.push_back(s); tail.push_back(s); left -= 2 * s;
+        }
+        sizes = head;
+        for (; left > 0; left -= B) sizes.push_back(std::min(B, left));
+        sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
+    }
+    int status = HSFLOW_OK, first = 0;
+    for (size_t i = 0; i < sizes.size() && status == HSFLOW_OK; first += sizes[i], ++i) {
+        const int slot = (int)(i % K), p0 = slot * slot_pairs, n = sizes[i];
         if (i >= K) CK(cudaStreamWaitEvent(h->s_in, ev_comp[slot], 0));      // frames of the slot were consumed
         if (sequence) {
             for (int k = 0; k <= n; ++k)
@@ -955,11 +996,16 @@ static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, in
         CK(cudaEventRecord(ev_in[slot], h->s_in));
         CK(cudaStreamWaitEvent(h->stream, ev_in[slot], 0));
         if (i >= K) CK(cudaStreamWaitEvent(h->stream, ev_out[slot], 0));     // u/v of the slot were read back
-        status = sequence ? compute_subbatch(h, p0, n, h->f1, h->f1 + h->f_pair_pitch) : compute_subbatch(h, p0, n);
+        float* su = planar ? h->stage + slot * slot_floats : nullptr;          // U block [n][H][W], then V block
+        float* sv = planar ? su + (size_t)n * px : nullptr;
+        status = sequence ? compute_subbatch(h, p0, n, h->f1, h->f1 + h->f_pair_pitch, su, sv) : compute_subbatch(h, p0, n, nullptr, nullptr, su, sv);
         if (status) break;
         CK(cudaEventRecord(ev_comp[slot], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, ev_comp[slot], 0));
-        for (int k = 0; k < n; ++k) {
+        if (planar) {
+            CK(cudaMemcpyAsync(u_out + (size_t)first * px, su, (size_t)n * px * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+            CK(cudaMemcpyAsync(v_out + (size_t)first * px, sv, (size_t)n * px * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+        } else for (int k = 0; k < n; ++k) {
             CK(cudaMemcpy2DAsync(u_out + (size_t)(first + k) * px, wb, h->uA + (size_t)(p0 + k) * h->uv_pp, h->uv_rp * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
             CK(cudaMemcpy2DAsync(v_out + (size_t)(first + k) * px, wb, h->vA + (size_t)(p0 + k) * h->uv_pp, h->uv_rp * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
         }
