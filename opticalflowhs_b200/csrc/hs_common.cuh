@@ -12,7 +12,6 @@
 
 namespace hs {
 
-constexpr int kLanePx = 4;      // pixels per lane (one float4)
 constexpr int kStripW = 128;    // columns one warp streams (32 lanes x 4 px)
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -128,11 +127,5 @@ __device__ __forceinline__ void clamp_lr(const float (&c)[4], int col0, int W, f
     if (col0 == 0) l = c[0];
     if (col0 + 3 == W - 1) r = c[3];
 }
-
-struct PlaneRef {       // fp32 plane set: [pair][row][col]
-    float* p;
-    long long row_pitch;   // elements
-    long long pair_pitch;  // elements
-};
 
 }  // namespace hs

@@ -5,27 +5,29 @@
 // u, v and the three coefficient planes once and writes u, v once.
 //
 // Design (B200-first, HBM-bound fp32 stencil -- no tensor cores on purpose):
-//  * work unit = one WARP x (128-column strip, row chunk, frame pair).  Warps are autonomous:
-//    own shared-memory rings, own mbarriers, no __syncthreads anywhere; one warp per CTA.
-//  * the fp32 planes are row-interleaved in HBM ([row][u|v][pitch], [row][a|b|c][pitch]), so ONE TMA
-//    operation (cp.async.bulk.tensor.4d, box = 128 columns x all planes x 2 rows, issued by one
-//    elected lane) refills a ring slot.  Out-of-image columns are zero-filled by the TMA unit and
-//    re-clamped in registers (Neumann border, Tex2D Kernels.cl:2-9): no bounds checks on loads.
-//  * the warp streams DOWN the rows.  Each lane owns 4 adjacent columns.  Time step s+1 of row
-//    r-1 is produced as soon as time step s of row r exists, so T time steps are in flight as a
-//    register pipeline: per stage and field only two partial sums per pixel are kept
-//    (p = G(r-1) + 2h(r), g = G(r); see hs_common.cuh), 16 registers per stage.
-//  * left/right neighbours come from warp shuffles (one __shfl_up + one __shfl_down per field
-//    and stage-row); the strip carries a halo of HL >= T columns on each side that absorbs the
-//    shrinking valid region, the chunk carries T warm-up rows above and below.
-//  * three code paths: a generic tick with run-time predicates (pipeline fill, bottom-edge drain,
-//    tiny frames) and two branch-free steady-state loops (interior strips / strips touching the
-//    left or right image edge), two ticks = one TMA row group per trip, ring positions and
-//    barrier phases kept incrementally.
-//  * results leave through coalesced 16-byte stores of the strip's valid columns.
-// Per pixel-iteration: 14 FP32 instructions, 1 shuffle, 12 B of shared-memory reads; HBM
-// traffic 28 B / T per pixel-iteration (+ halo overhead; measured 29 B per pixel and launch at T=4).
-// tests/stream_model.py is the numpy model of exactly this bookkeeping.
+//  * work unit = one WARP x (128-column strip, row chunk, frame pair).  Warps are autonomous: own shared-memory
+//    rings, own mbarriers, no __syncthreads anywhere.  A CTA is exactly one warp, so the unit index is blockIdx.x and
+//    the whole geometry is warp-uniform by construction (uniform registers, uniform datapath).
+//  * the fp32 planes are row-interleaved in HBM ([row][u|v][pitch], [row][a|b|c][pitch]), so ONE TMA operation
+//    (cp.async.bulk.tensor.4d, box = 128 columns x all planes x RG rows, issued by one elected lane) refills a ring
+//    slot.  Out-of-image columns are zero-filled by the TMA unit and re-clamped in registers (Neumann border, Tex2D
+//    Kernels.cl:2-9): no bounds checks on loads.
+//  * the warp streams DOWN the rows.  Each lane owns 4 adjacent columns.  Time step s+1 of row r-1 is produced as
+//    soon as time step s of row r exists, so T time steps are in flight as a register pipeline: per stage and
+//    field only two partial sums per pixel are kept (p = G(r-1) + 2h(r), g = G(r); see hs_common.cuh), held as
+//    packed pixel pairs for FFMA2 / FADD2 / FMUL2: 16 registers per stage.
+//  * left/right neighbours come from warp shuffles (one __shfl_up + one __shfl_down per field and stage-row); the
+//    strip carries a halo of HL >= T columns on each side that absorbs the shrinking valid region, the chunk carries
+//    T warm-up rows above and below.
+//  * two code paths: a generic tick with run-time predicates (pipeline fill, bottom-edge drain, tiny frames) and a
+//    branch-free steady-state loop (interior strips / strips touching the left or right image edge), RG ticks = one
+//    TMA row group per trip, every shared-memory address "register + immediate", ring pointers, barrier phases and
+//    TMA coordinates advanced once per trip.
+//  * results leave through coalesced 16-byte stores of the strip's valid columns -- into the partner buffer, into a
+//    planar staging slot (host pipeline), and a second time into the neighbour strips over NVLink (PEER).
+// Per stage-row (128 pixels x 1 iteration) a lane issues 49-50 instructions at T = 4..6, of which 32 are FP32 math, 4
+// shuffles and 3 LDS.128; HBM traffic is 28 B / T per pixel-iteration (+ halo overhead: 29.2 B per pixel and launch
+// measured at T = 6).  tests/stream_model.py is the numpy model of exactly this bookkeeping.
 #include <type_traits>
 #include <utility>
 
@@ -62,12 +64,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (!ok && ++spins > (1u << 22)) __trap();   // a lost TMA transaction must fail loudly, never hang the GPU
     } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int x, int y, int z, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(bar)
-        : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int x, int pl, int y, int z, uint32_t bar) {
     asm volatile(

@@ -678,10 +678,8 @@ int hsflow_halo_refreshed(hsflow_t* h) { NEED(h); h->valid_lo = 0; h->valid_hi =
 static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nullptr, const uint8_t* f2base = nullptr,
                             float* fin_u = nullptr, float* fin_v = nullptr) {
     const int T = effective_T(h), N = h->iterations;
-    const bool streamk = use_stream_kernel(h, std::min(T, std::max(N, 1)));
     int L = 0;                                     // ping-pong flips
     for (int left = N; left > 0;) { const int t = std::min(left, T); L += use_stream_kernel(h, t) ? 1 : t; left -= t; }
-    (void)streamk;
     const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
     int rc = run_deriv(h, p0, n, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp, f1base, f2base);
     if (rc) return rc;
