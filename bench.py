@@ -230,7 +230,7 @@ def run_ours(args, rank, world, local_rank):
     value = px_it_step * args.steps / (ms_max * 1e-3) / 1e6
 
     # ---- roofline leg: the dominant kernel alone, one sub-batch, same shape as in the run ----------
-    sub = min(pairs, 32)
+    sub = eng.sub_batch                           # pairs per launch in the run above
     eng.configure(W4K, H4K, sub).synth_frames(0, 0, 999)
     eng.prepare(); eng.iterate(ITER); eng.sync()
     reps = []
@@ -288,7 +288,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"synthetic {W4K}x{H4K} gray8 frame pairs, alpha={ALPHA:g}, {ITER} iterations, FULL mode "
                                    f"(u and v updated), {pairs} pairs per GPU sharded by pair (BASELINE.json configs[3])",
-                       "pairs_per_gpu": pairs, "temporal_block": T_eff, "math": "fast",
+                       "pairs_per_gpu": pairs, "pairs_per_launch": sub, "temporal_block": T_eff, "math": "fast",
                        "cache": "working set per step >> 126 MB L2 (no flush needed)"},
             "pairs_4k100_per_s": value * 1e6 / (W4K * H4K * ITER),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

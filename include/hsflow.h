@@ -170,6 +170,7 @@ long long hsflow_kernel_launches(hsflow_t* h);        /* kernels launched by thi
 int hsflow_iterations_done(hsflow_t* h, int pair, int* done);  /* sweeps a pair ran since prepare (< iterations
                                                                    when hsflow_set_epsilon stopped it).  sync */
 int hsflow_effective_temporal_block(hsflow_t* h);
+int hsflow_sub_batch(hsflow_t* h);                    /* pairs per launch chosen by hsflow_configure          */
 void* hsflow_alloc_pinned(size_t bytes);              /* cudaMallocHost / cudaFreeHost helpers     */
 void hsflow_free_pinned(void* p);
 

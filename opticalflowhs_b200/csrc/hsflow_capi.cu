@@ -345,11 +345,25 @@ int hsflow_configure(hsflow_t* h, int W, int H, int P) {
     CK(cudaStreamSynchronize(h->stream));
     free_planes(h);
     h->W = W; h->H = H; h->P = P;
-    h->S = h->sub_batch > 0 ? std::min(h->sub_batch, P) : std::min(P, 32);
     h->pitch = ((long long)W + 31) / 32 * 32;
     h->uv_rp = 2 * h->pitch; h->uv_pp = h->uv_rp * H;
     h->c_rp = 3 * h->pitch; h->c_pp = h->c_rp * H;
     h->top_edge = h->bottom_edge = 1;
+    // Pairs per launch (the scratch sub-batch: ping-pong partner + coefficient planes, 20 B/px per pair).  As many as
+    // fit: one launch over 256 4K pairs runs 8 waves of work units that drift apart and keep HBM and the SMs busy
+    // through each other's fill and drain phases -- 1 014 k Mpixel-iterations/s against 916 k for eight launches of 32
+    // pairs (tools/subbatch_probe.py).  Auto: everything, unless results + frames + scratch would take more than
+    // half of the free device memory (256 4K pairs: 64 GB of 180).
+    if (h->sub_batch > 0) h->S = std::min(h->sub_batch, P);
+    else {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+        const double per_pair = (double)(h->uv_pp + h->c_pp) * sizeof(float);
+        const double fixed = ((double)h->uv_pp * sizeof(float) + 8.0 * W * H) * P;       // results + two frames of <= 4 B/px
+        const double room = 0.5 * (double)free_b - fixed;
+        h->S = (int)std::max(1.0, std::min((double)P, room / per_pair));
+        if (free_b == 0) h->S = std::min(P, 32);
+    }
     const size_t uvP = (size_t)h->uv_pp * P * sizeof(float), uvS = (size_t)h->uv_pp * h->S * sizeof(float);
     const size_t cS = (size_t)h->c_pp * h->S * sizeof(float);
     if (cudaMalloc(&h->uA, uvP) != cudaSuccess || cudaMalloc(&h->uB, uvS) != cudaSuccess ||
@@ -1056,6 +1070,7 @@ float hsflow_last_ms(hsflow_t* h, int phase) {
     return ms;
 }
 long long hsflow_kernel_launches(hsflow_t* h) { return h ? h->launches : 0; }
+int hsflow_sub_batch(hsflow_t* h) { return h ? h->S : 0; }
 int hsflow_iterations_done(hsflow_t* h, int pair, int* done) {
     NEED(h);
     if (pair < 0 || pair >= h->P || !done) return fail(HSFLOW_EINVAL, "bad argument");

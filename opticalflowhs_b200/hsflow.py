@@ -74,6 +74,7 @@ SIGNATURES = {
     "hsflow_kernel_launches": (C.c_longlong, [_P]),
     "hsflow_iterations_done": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "hsflow_effective_temporal_block": (C.c_int, [_P]),
+    "hsflow_sub_batch": (C.c_int, [_P]),
     "hsflow_alloc_pinned": (_P, [C.c_size_t]),
     "hsflow_free_pinned": (None, [_P]),
 }
@@ -300,6 +301,10 @@ class HSFlow:
     @property
     def kernel_launches(self):
         return self._L.hsflow_kernel_launches(self._h)
+
+    @property
+    def sub_batch(self):
+        return self._L.hsflow_sub_batch(self._h)
 
     @property
     def temporal_block(self):
