@@ -174,6 +174,31 @@ def run_reference(args, rank):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this rank's threads (and with them its pinned host buffers, which are placed on the allocating thread's
+    node) to the CPU socket its GPU hangs off: with 8 ranks the host-buffer traffic of the e2e leg otherwise crosses
+    the socket interconnect.  Best effort: returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -183,6 +208,8 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank)
+    print(f"[bench] rank {rank}: GPU {local_rank} on host NUMA node {numa_node}, {len(os.sched_getaffinity(0))} CPUs", file=sys.stderr)
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -298,8 +325,9 @@ def run_ours(args, rank, world, local_rank):
                                  "ncu dram bytes are in profiles/"},
             "cpu_baseline": cpu,
             "cpu_baseline_opencv": cpu_cv,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W4K * H4K * ep,
-                    "d2h_bytes_per_step": 8 * W4K * H4K * ep, "pairs_per_step": ep, "api": "hsflow_run_batch_host",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W4K * H4K * ep * world,
+                    "d2h_bytes_per_step": 8 * W4K * H4K * ep * world, "pairs_per_step": ep * world, "api": "hsflow_run_batch_host",
+                    "host_numa_node_rank0": numa_node,
                     "result_checksum": result_checksum},
             "gpu_launches": int(launches),
             "clocks": clocks,
