@@ -499,17 +499,21 @@ static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* 
     return HSFLOW_OK;
 }
 
-// Rows per work unit.  A unit streams chunk + 2T rows (T warm-up rows above and below; those 2T ticks run in the
-// generic, predicated path at roughly a third of the steady-state speed) plus a fixed prologue worth about 4 rows,
-// and a launch runs ceil(units / resident warps) waves of units one after the other: pick the chunk height that
-// minimises   waves x (chunk + 6T + 4).   With many units this is "least redundant work, fullest last wave"; with
-// few (one small frame) it makes the single wave as short as possible.  Heights are multiples of the TMA box rows
-// so that every chunk enters the steady state without extra generic ticks (1080p, T = 4: 464 us per 100 iterations
-// with 16-row chunks, 544 us with 15).
+// Rows per work unit.  A unit streams chunk + 2T rows (T warm-up rows above and below; those ticks run in the
+// generic, predicated path at about half the steady-state speed) plus a fixed prologue worth about 4 rows, and a
+// launch runs ceil(units / resident warps) waves of units one after the other: pick the chunk height that minimises
+//   waves x (chunk + 4T + 4) x (1 + 0.2 / waves).
+// The last factor is the lockstep penalty of short launches: in a single wave every warp runs its pipeline fill, its
+// steady state and its drain at the same time as all the others, with several waves the units drift apart and keep
+// HBM and the SMs busy through each other's phases (one 16384^2 frame, T = 6: 14.15 ms per 60 iterations with 1 wave
+// of 2049-row chunks, 13.28 ms with 4 waves of 513-row chunks; 32 4K pairs: 14.75 -> 13.8 ms).  With many units the
+// rule is "least redundant work, fullest last wave"; with few (one small frame) it makes the single wave as short as
+// possible.  Heights are multiples of the TMA box rows so that every chunk enters the steady state without extra
+// generic ticks (1080p, T = 4: 464 us per 100 iterations with 16-row chunks, 544 us with 15).
 static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T) {
     if (h->chunk_rows > 0) return std::min(h->chunk_rows, rows);
     const long long slots = (long long)h->sm_count * std::max(1, stream_warps_per_sm(T, h->stencil));
-    long long best = -1;
+    double best = -1.0;
     int best_ch = rows;
     const int rg = stream_geometry(T).rows_per_box;
     for (int ncy = 1; ncy <= rows; ++ncy) {
@@ -517,8 +521,8 @@ static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T) 
         if (ch < 8 && ncy > 1) break;
         const long long units = (long long)nsx * ((rows + ch - 1) / ch) * pairs;
         const long long waves = (units + slots - 1) / slots;
-        const long long cost = waves * (ch + 6LL * T + 4);
-        if (best < 0 || cost < best) { best = cost; best_ch = ch; }
+        const double cost = (double)waves * (ch + 4.0 * T + 4.0) * (1.0 + 0.2 / (double)waves);
+        if (best < 0 || cost < best - 1e-9) { best = cost; best_ch = ch; }
         if (ncy > 4096) break;
     }
     return best_ch;
