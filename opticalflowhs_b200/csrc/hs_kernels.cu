@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(128) k_deriv(DerivArgs A) {
         et = __fmul_rn(q, et);
         if (A.normalise) normalise_coefs(ex, ey, et, A.rho, o0[k], o1[k], o2[k]);
         else { o0[k] = ex; o1[k] = ey; o2[k] = et; }
+        if (A.zero_b) o1[k] = 0.f;
     }
     const size_t o = (size_t)z * A.c_pair_pitch + (size_t)j * A.c_row_pitch + x;
     *reinterpret_cast<float4*>(A.c0 + o) = make_float4(o0[0], o0[1], o0[2], o0[3]);
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) k_deriv_cv(DerivArgs A) {
     float et = (float)((int)f2[(size_t)y * A.f_row_pitch + x] - (int)r1[x]);
     float o0 = ex, o1 = ey, o2 = et;
     if (A.normalise) normalise_coefs(ex, ey, et, A.rho, o0, o1, o2);
+    if (A.zero_b) o1 = 0.f;
     const size_t o = (size_t)blockIdx.z * A.c_pair_pitch + (size_t)y * A.c_row_pitch + x;
     A.c0[o] = o0; A.c1[o] = o1; A.c2[o] = o2;
 }

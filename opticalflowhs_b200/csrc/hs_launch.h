@@ -18,6 +18,7 @@ struct DerivArgs {
     long long c_pair_pitch;     // elements
     int W, H;
     int normalise;              // 1: write a,b,c = (Ex,Ey,Et)/sqrt(rho+Ex^2+Ey^2); 0: raw derivatives
+    int zero_b;                 // 1: store b = 0 (LITERAL mode on the streaming kernel, see literal_on_stream in hsflow_capi.cu)
     float rho;                  // alpha^2 (Kernels.cl:85) or 1/lambda
 };
 

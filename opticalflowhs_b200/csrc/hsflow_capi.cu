@@ -116,6 +116,8 @@ struct hsflow {
     float* stage = nullptr;
     size_t stage_bytes = 0;
     float *ov_u = nullptr, *ov_v = nullptr;        // output override of the launch run_block issues next
+    int uv_dirty = 0;                              // hsflow_write_uv stored a v field since the last zeroing
+    int coef_zero_b = 0;                           // the coefficient planes in memory were written with b = 0
 };
 
 static void strip_disconnect(hsflow* h) {
@@ -152,13 +154,22 @@ static int auto_T(const hsflow* h) {
     const long long units = nsx * ((h->H + 4 * kDefaultT - 1) / (4 * kDefaultT)) * std::max(1, std::min(h->P, h->S));
     return units >= 2LL * h->sm_count * 8 ? kDefaultT : kSmallT;
 }
+// LITERAL mode (update_v = 0: the shipped u_v_updateKernel never writes v, Kernels.cl:87-89) on the FULL streaming
+// kernel.  While v is identically zero, "v stays what it was" and "v' = vbar - b t with b = 0" are the same thing, and
+// t = a ubar + b vbar + c is a ubar + c either way: the derivative pass stores b = 0 (the normalisation still uses
+// Ex^2 + Ey^2) and the temporally blocked kernel runs unchanged -- bit-identical to k_jacobi1<.., UPDATE_V = false>
+// (fma(b, +0, c) == c == fma(0, +0, c) since c is never -0), 17 launches per 100 iterations instead of 100.
+// Needs v == 0: no warm start, no hsflow_write_uv of a v field.
+static bool literal_on_stream(const hsflow* h) {
+    return !h->update_v && h->math == HSFLOW_MATH_FAST && !h->warm && !h->uv_dirty;
+}
 static int effective_T(const hsflow* h) {
-    if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1 || h->eps > 0.0) return 1;
+    if (h->math == HSFLOW_MATH_EXACT || (!h->update_v && !literal_on_stream(h)) || h->kernel_sel == 1 || h->eps > 0.0) return 1;
     int T = h->tblock > 0 ? h->tblock : auto_T(h);
     return std::min(T, kMaxT);
 }
 static bool use_stream_kernel(const hsflow* h, int t) {
-    if (h->math == HSFLOW_MATH_EXACT || !h->update_v || h->kernel_sel == 1 || h->eps > 0.0) return false;
+    if (h->math == HSFLOW_MATH_EXACT || (!h->update_v && !literal_on_stream(h)) || h->kernel_sel == 1 || h->eps > 0.0) return false;
     (void)t;                                       // also for a single iteration: at T = 1 the TMA-fed streaming kernel
     return true;                                   // moves 5.3 TB/s where k_jacobi1 moves 4.6-4.8 (tools/gpu_perf_probe.py)
 }
@@ -475,6 +486,7 @@ static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* 
     A.c0 = o0; A.c1 = o1; A.c2 = o2;
     A.c_row_pitch = c_rp; A.c_pair_pitch = c_pp;
     A.W = h->W; A.H = h->H; A.normalise = normalise; A.rho = h->rho;
+    A.zero_b = h->coef_zero_b;
     if (h->deriv == HSFLOW_DERIV_CL) {
         A.f1 = f1base + (size_t)p0 * h->f_pair_pitch;
         A.f2 = f2base + (size_t)p0 * h->f_pair_pitch;
@@ -607,6 +619,8 @@ int hsflow_prepare(hsflow_t* h) {
     CK(cudaSetDevice(h->device));
     phase_begin(h, HSFLOW_PHASE_DERIV);
     const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
+    if (!h->warm) h->uv_dirty = 0;                 // u, v are zeroed below
+    h->coef_zero_b = (!h->update_v && use_stream_kernel(h, 1)) ? 1 : 0;
     int rc = run_deriv(h, 0, h->P, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp);
     if (rc) return rc;
     h->coef_norm = norm;
@@ -699,6 +713,7 @@ static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nu
     int L = 0;                                     // ping-pong flips
     for (int left = N; left > 0;) { const int t = std::min(left, T); L += use_stream_kernel(h, t) ? 1 : t; left -= t; }
     const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
+    h->coef_zero_b = (!h->update_v && use_stream_kernel(h, 1)) ? 1 : 0;     // u, v are zeroed below: only warm / dirty say no
     int rc = run_deriv(h, p0, n, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp, f1base, f2base);
     if (rc) return rc;
     h->coef_norm = norm;
@@ -867,6 +882,14 @@ int hsflow_write_uv(hsflow_t* h, int pair, const float* u, const float* v, size_
     if (pitch == 0) pitch = wb;
     if (u) CK(cudaMemcpy2DAsync(cur_u(h) + (size_t)pair * h->uv_pp, h->uv_rp * sizeof(float), u, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
     if (v) CK(cudaMemcpy2DAsync(cur_v(h) + (size_t)pair * h->uv_pp, h->uv_rp * sizeof(float), v, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
+    if (v) {
+        h->uv_dirty = 1;                           // LITERAL mode leaves the streaming kernel (literal_on_stream)
+        if (h->coef_zero_b && h->prepared && h->P <= h->S) {   // ... and needs the true b plane again
+            h->coef_zero_b = 0;
+            int rc = run_deriv(h, 0, h->P, h->coef_norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp);
+            if (rc) return rc;
+        }
+    }
     CK(cudaStreamSynchronize(h->stream));
     return HSFLOW_OK;
 }
@@ -882,7 +905,10 @@ int hsflow_read_derivatives(hsflow_t* h, int pair, float* Ex, float* Ey, float* 
         return fail(HSFLOW_ENOMEM, "cudaMalloc");
     }
     float* d[3] = {h->dtmp, h->dtmp + plane, h->dtmp + 2 * plane};
+    const int keep_zero_b = h->coef_zero_b;
+    h->coef_zero_b = 0;                            // the caller gets Ex, Ey, Et as ComputeDerivativesKernel writes them
     int rc = run_deriv(h, pair, 1, 0, d[0], d[1], d[2], h->pitch, plane);
+    h->coef_zero_b = keep_zero_b;
     if (rc) return rc;
     float* o[3] = {Ex, Ey, Et};
     for (int k = 0; k < 3; ++k)

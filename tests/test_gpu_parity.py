@@ -193,6 +193,42 @@ def test_stream_kernel_bit_identical_to_single_sweep(eng, P, T):
             assert (bits(out[0]) == bits(ref[0])).all() and (bits(out[1]) == bits(ref[1])).all(), (h, w, T, chunk, wpc)
 
 
+@pytest.mark.parametrize("T", [1, 4, 6])
+def test_literal_mode_on_the_stream_kernel_bit_identical_to_single_sweep(eng, P, oracle, T):
+    """update_v = 0 (the shipped kernel never writes v, Kernels.cl:87-89) runs on the temporally blocked kernel with a
+    zeroed b plane while v == 0; it must equal the single-sweep LITERAL kernel bit for bit and stay within the
+    tolerance of the oracle; a v field written by the caller sends it back to the single-sweep kernel."""
+    rng = np.random.default_rng(300 + T)
+    for (h, w) in [(1, 1), (5, 116), (40, 124), (37, 250), (70, 131)]:
+        g1, g2 = rand_frames(rng, h, w)
+        n = 2 * T + 1
+        eng.set_math(P.MATH_FAST).set_kernel(1).set_params(15.0, n, P.STENCIL_CL8, False, 1)
+        eng.load_pair(g1, g2).compute()
+        ref = eng.read_uv()
+        eng.set_kernel(0).set_params(15.0, n, P.STENCIL_CL8, False, T)
+        assert eng.temporal_block == T
+        eng.load_pair(g1, g2).compute()
+        out = eng.read_uv()
+        assert (bits(out[0]) == bits(ref[0])).all() and not out[1].any(), (h, w, T)
+        uo, vo = oracle.run_cl(g1, g2, 15.0, n, False)
+        assert np.abs(out[0] - uo).max() <= TOL_MAX and not vo.any()
+        ex, ey, et = eng.read_derivatives()             # still the raw derivatives, Ey included
+        assert np.abs(ey).max() > 0 or h == 1
+    # a caller-supplied v field: v is no longer zero, the iteration has to keep it constant (single-sweep kernel)
+    g1, g2 = rand_frames(rng, 40, 124)
+    v0 = rng.standard_normal((40, 124)).astype(np.float32)
+    d = oracle.derivatives(g1.astype(np.float32), g2.astype(np.float32))
+    uo, vo = oracle.jacobi(*d, 15.0, 9, update_v=False, u0=np.zeros_like(v0), v0=v0)
+    eng.set_kernel(0).set_params(15.0, 9, P.STENCIL_CL8, False, T)
+    eng.load_pair(g1, g2).prepare()
+    eng.write_uv(np.zeros_like(v0), v0)
+    assert eng.temporal_block == 1
+    eng.iterate(9)
+    u, v = eng.read_uv()
+    assert (bits(v) == bits(v0)).all() and np.abs(u - uo).max() <= TOL_MAX
+    eng.set_kernel(0)
+
+
 @pytest.mark.parametrize("T", [2, 4, 7])
 def test_stream_kernel_cv4_stencil_bit_identical(eng, P, T):
     rng = np.random.default_rng(7 + T)
