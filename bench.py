@@ -13,7 +13,8 @@ A "step" is one pass of the hot path (derivatives + 100 iterations) over the ran
   e2e       same metric through hsflow_run_batch_host: pinned host frames in, u/v back to pinned
             host memory every step (H2D + D2H inside the timed region, overlapped with compute)
   roofline  dominant kernel k_jacobi_stream<T>: algorithmic (unfused-equivalent) bytes
-            28 B x pixels x T per launch / measured launch time, against MEASURED_PEAKS.json
+            28 B x pixels x T per launch / launch time measured with CUDA events inside the timed
+            region (iteration phase of the last timed step / launches), against MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the reference's own Kernels.cl compiled for the host
             (oracle/_ref/libclref.so, OpenMP over rows = what its CL_DEVICE_TYPE_CPU path does),
             bounded sample, on the box's host cores.  oracle/ is only ever the thing timed here,
@@ -256,17 +257,18 @@ def run_ours(args, rank, world, local_rank):
     px_it_step = float(W4K) * H4K * ITER * pairs * world
     value = px_it_step * args.steps / (ms_max * 1e-3) / 1e6
 
-    # ---- roofline leg: the dominant kernel alone, one sub-batch, same shape as in the run ----------
-    sub = eng.sub_batch                           # pairs per launch in the run above
-    eng.configure(W4K, H4K, sub).synth_frames(0, 0, 999)
-    eng.prepare(); eng.iterate(ITER); eng.sync()
-    reps = []
-    for _ in range(3):
-        eng.prepare(); eng.iterate(ITER); eng.sync()
-        reps.append(eng.last_ms(2))
-    n_launch = (ITER + T_eff - 1) // T_eff
-    launch_ms = statistics.median(reps) / n_launch
-    alg_bytes = ALG_BYTES_PER_PX_IT * W4K * H4K * sub * (ITER / n_launch)
+    # ---- roofline leg: the dominant kernel inside the timed region ------------------------------------
+    # The engine brackets the iteration phase of every hsflow_compute with CUDA events on its own stream
+    # (HSFLOW_PHASE_ITER); the last timed step's phase = ceil(ITER / T) back-to-back launches of k_jacobi_stream
+    # over `sub` pairs each (when the batch does not fit one launch the phase covers all sub-batches).
+    sub = eng.sub_batch                           # pairs per launch
+    n_launch = (ITER + T_eff - 1) // T_eff * ((pairs + sub - 1) // sub)
+    iter_ms = eng.last_ms(2)
+    if iter_ms <= 0:                              # no event pair (should not happen): time one more step alone
+        eng.compute(); eng.sync()
+        iter_ms = eng.last_ms(2)
+    launch_ms = iter_ms / n_launch
+    alg_bytes = ALG_BYTES_PER_PX_IT * W4K * H4K * pairs * ITER / n_launch
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     traffic = None                                # ncu dram bytes per launch, scaled from the committed capture
@@ -274,7 +276,7 @@ def run_ours(args, rank, world, local_rank):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             rec = json.load(f).get(f"k_jacobi_stream<T={T_eff}>")
         if rec:
-            traffic = rec["dram_bytes_per_pixel_launch"] * W4K * H4K * sub
+            traffic = rec["dram_bytes_per_pixel_launch"] * W4K * H4K * pairs / ((pairs + sub - 1) // sub)
     except Exception:
         traffic = None
 
