@@ -32,6 +32,14 @@ def test_header_symbols_are_exported_and_bound():
     assert L.hsflow_version() >= 100
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/hsflow.h is the C ABI: it has to compile as C99 (cgo / JNI / ctypes-generator consumers), not only as C++."""
+    src = tmp_path / "hc.c"
+    src.write_text('#include "%s"\nint main(void) { hsflow_t* h = 0; hsflow_strip_handle_t s; (void)s; '
+                   'return hsflow_version() > 0 && h == 0 ? 0 : 1; }\n' % os.path.join(ROOT, "include", "hsflow.h"))
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-c", str(src), "-o", str(tmp_path / "hc.o")])
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
