@@ -288,18 +288,22 @@ def test_device_synthetic_frames_equal_oracle_generator(P, oracle):
             assert (bits(x) == bits(y)).all()
 
 
-def test_pipelined_host_batch_equals_per_pair_compute(P, oracle):
-    W, H, n = 256, 120, 11
+@pytest.mark.parametrize("W,H,n,math_exact", [(256, 120, 11, False), (232, 64, 41, False), (250, 60, 41, False), (128, 48, 37, True)])
+def test_pipelined_host_batch_equals_per_pair_compute(P, oracle, W, H, n, math_exact):
+    """hsflow_run_batch_host against loading every pair separately: one sub-batch; ramped sub-batch sizes with planar
+    staging (W % 4 == 0, streaming kernel); the 2-D copy fallback for W % 4 != 0 and for the single-sweep kernel."""
     frames = np.empty((n, 2, H, W), np.uint8)
     for k in range(n):
         frames[k, 0], frames[k, 1] = oracle.synth_pair(W, H, seed=50 + k)
     u = np.empty((n, H, W), np.float32)
     v = np.empty((n, H, W), np.float32)
+    math = P.MATH_EXACT if math_exact else P.MATH_FAST
     with P.HSFlow(0) as e:
-        e.set_params(15.0, 12, P.STENCIL_CL8, True, 4)
+        e.set_math(math).set_params(15.0, 12, P.STENCIL_CL8, True, 4)
         e.run_batch_host(frames, u, v)
+        e.run_batch_host(frames, u, v)                  # slots and staging are reused
     with P.HSFlow(0) as e:
-        e.set_params(15.0, 12, P.STENCIL_CL8, True, 4)
+        e.set_math(math).set_params(15.0, 12, P.STENCIL_CL8, True, 4)
         for k in range(n):
             e.load_pair(frames[k, 0], frames[k, 1]).compute()
             us, vs = e.read_uv()
