@@ -97,6 +97,25 @@ class ClockSampler:
 # reference arm / cpu baseline: Kernels.cl on the host cores
 # ------------------------------------------------------------------------------------------------
 
+def host_cores():
+    """Host threads this process may use.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which made the reference arm of the N > 1 runs single-threaded in round 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_config(pairs):
+    """The `config` object, IDENTICAL in both arms (ours and --impl reference): it names the workload, nothing else.
+    What each arm did with it (pairs per launch, temporal block, sample size) is reported outside of it."""
+    return {"workload": f"synthetic {W4K}x{H4K} gray8 frame pairs, alpha={ALPHA:g}, {ITER} iterations, FULL mode (u and v "
+                        f"updated), {pairs} pairs per GPU sharded by pair (BASELINE.json configs[3])",
+            "width": W4K, "height": H4K, "iterations": ITER, "alpha": ALPHA, "mode": "FULL", "stencil": "CL8",
+            "pairs_per_gpu": pairs, "sharding": "pairs",
+            "cache": "working set per step >> 126 MB L2 (no flush needed)"}
+
+
 def cpu_reference_rate(target_seconds, threads=None):
     """Mpixel-iterations/s of the reference's kernels on the host (one 4K pair, bounded iterations)."""
     import numpy as np
@@ -104,7 +123,7 @@ def cpu_reference_rate(target_seconds, threads=None):
     O.build()
     f1, f2 = O.synth_pair(W4K, H4K, seed=1234)
     kind = "reference" if O.have_ref() else "port"
-    cores = threads or O.max_threads()
+    cores = threads or host_cores()
     O.set_threads(cores)
     run = (lambda n: O.ref_run(f1, f2, ALPHA, n, True)) if kind == "reference" else (lambda n: O.run_cl(f1, f2, ALPHA, n, True))
     t0 = time.perf_counter(); run(2); t2 = time.perf_counter() - t0          # calibration: derivative pass + 2 iterations
@@ -135,7 +154,7 @@ def cpu_opencv_rate(target_seconds):
     f1, f2 = O.synth_pair(W4K, H4K, seed=1234)
     out = {"unit": UNIT, "kind": "port", "lambda": 0.1,
            "what": "restated OpenCV 2.1 cvCalcOpticalFlowHS incl. both cvSmooth calls, 4-neighbour stencil, eps = 1e-6"}
-    for label, threads in (("one_thread", 1), ("all_threads", O.max_threads())):
+    for label, threads in (("one_thread", 1), ("all_threads", host_cores())):
         O.set_threads(threads)
         t0 = time.perf_counter(); O.run_cv(f1, f2, 0.1, 2, eps=1e-6); t2 = time.perf_counter() - t0
         t0 = time.perf_counter(); O.run_cv(f1, f2, 0.1, 4, eps=1e-6); t4 = time.perf_counter() - t0
@@ -144,7 +163,7 @@ def cpu_opencv_rate(target_seconds):
         t0 = time.perf_counter(); _, _, done = O.run_cv(f1, f2, 0.1, n, eps=1e-6); dt = time.perf_counter() - t0
         out[label] = {"value": W4K * H4K * done / dt / 1e6, "cores": threads,
                       "sample": f"1 synthetic {W4K}x{H4K} pair x {done} iterations (of {ITER}), {dt:.1f} s"}
-    O.set_threads(O.max_threads())
+    O.set_threads(host_cores())
     return out
 
 
@@ -162,8 +181,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(d for _, d in vals), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {W4K}x{H4K} frame pairs, alpha={ALPHA:g}, {ITER} iterations, FULL mode; "
-                               "reference arm = Kernels.cl compiled for the host, bounded sample per step"},
+        "config": workload_config(args.pairs),
+        "arm": "Kernels.cl compiled for the host (oracle/_ref/libclref.so), OpenMP over rows on every host core this process "
+               "may use, bounded sample of the workload per step",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[0], "kind": info[1], "sample": info[2]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -271,14 +291,32 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = ALG_BYTES_PER_PX_IT * W4K * H4K * pairs * ITER / n_launch
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
-    traffic = None                                # ncu dram bytes per launch, scaled from the committed capture
+    # Physical view beside the unfused-equivalent one: bytes a launch really has to move (fused minimum: u, v, three
+    # coefficient planes in, u, v out = 28 B per pixel and LAUNCH) and the DRAM bytes ncu counted for this kernel
+    # (profiles/traffic.json, a committed `ncu --set full` capture of the same launch shape, scaled per pixel).
+    px_launch = float(W4K) * H4K * pairs / ((pairs + sub - 1) // sub)
+    fused_min_bytes = ALG_BYTES_PER_PX_IT * px_launch
+    traffic = traffic_src = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             rec = json.load(f).get(f"k_jacobi_stream<T={T_eff}>")
         if rec:
-            traffic = rec["dram_bytes_per_pixel_launch"] * W4K * H4K * pairs / ((pairs + sub - 1) // sub)
+            traffic = rec["dram_bytes_per_pixel_launch"] * px_launch
+            traffic_src = rec.get("source", "profiles/traffic.json")
     except Exception:
         traffic = None
+
+    # ---- parity of the timed configuration: windows of the first and the last pair of THIS batch ------------
+    # (checked against the oracle after the engine is closed; the oracle never runs inside a timed region)
+    K = 32
+    spots = [(0, 0), (H4K // 2 - K // 2, 9 * (128 - 2 * ((T_eff + 3) // 4 * 4)) - K // 2), (H4K - K, W4K - K)]
+    windows = []
+    if rank == 0:
+        for z in (0, pairs - 1):
+            u, v = eng.read_uv(z)
+            for (y, x) in spots:
+                windows.append((z, y, x, u[y:y + K, x:x + K].copy(), v[y:y + K, x:x + K].copy()))
+            del u, v
 
     # ---- e2e: pinned host frames in, u/v back to pinned host memory, every step ---------------------
     ep = min(args.e2e_pairs, pairs)
@@ -290,22 +328,69 @@ def run_ours(args, rank, world, local_rank):
     for k in range(ep):
         frames[k, 0] = np.roll(base, 5 * k, axis=1)
         frames[k, 1] = np.roll(frames[k, 0], (1, 2), axis=(0, 1))
-    eng.run_batch_host(frames, uo, vo)           # warm-up (allocations, first touch)
-    barrier()
-    e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.run_batch_host(frames, uo, vo)       # returns when u/v are in host memory
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = float(W4K) * H4K * ITER * ep * world * e2e_steps / float(t.item()) / 1e6
-    result_checksum = float(uo[0, ::64, ::64].sum())
+
+    def time_e2e(call):
+        call()                                       # warm-up (allocations, first touch)
+        barrier()
+        e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call()                                   # returns when the results are in host memory
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(W4K) * H4K * ITER * ep * world * e2e_steps / float(t.item()) / 1e6
+
+    l_e2e0 = eng.kernel_launches
+    e2e_value = time_e2e(lambda: eng.run_batch_host(frames, uo, vo))
+    l_e2e = eng.kernel_launches - l_e2e0
+    e2e_windows = []
+    if rank == 0:
+        for k in (0, ep - 1):
+            y, x = 1000, 2000
+            e2e_windows.append((k, y, x, uo[k, y:y + K, x:x + K].copy(), vo[k, y:y + K, x:x + K].copy(), frames[k, 0].copy(), frames[k, 1].copy()))
+    # the consumer-shaped form: only the stride-4 samples the reference's consumer reads (cpp:762-767) cross PCIe
+    STEP = 4
+    us = pinned_empty((ep, H4K // STEP, W4K // STEP), np.float32)
+    vs = pinned_empty((ep, H4K // STEP, W4K // STEP), np.float32)
+    e2e_sampled = time_e2e(lambda: eng.run_pipeline_host(frames, us, vs, sample_step=STEP))
+    sampled_ok = bool((us[0] == uo[0, ::STEP, ::STEP]).all() and (vs[ep - 1] == vo[ep - 1, ::STEP, ::STEP]).all())
     eng.close()
+    del us, vs
+
+    # ---- the box's own copy ceiling with all N ranks copying at once (plain pinned cudaMemcpyAsync) --------
+    wire = pcie_ceiling(torch, dist, barrier)
+    wire_bound = None
+    if wire and wire.get("d2h_gbs_concurrent"):
+        t_wire = 8.0 * W4K * H4K * ep / (wire["d2h_gbs_concurrent"] * 1e9)          # per rank, u and v of one step
+        wire_bound = float(W4K) * H4K * ITER * ep * world / t_wire / 1e6
+    del frames, uo, vo
+
+    # ---- BASELINE.json configs[4] rides along: the strip-sharded 16K frame at this N ----------------------
+    strip = None
+    if not args.no_strip:
+        try:
+            strip = strip16k_record(args, torch, dist, rank, world, local_rank, barrier)
+        except Exception as ex:                     # the headline must survive a failure of the side record
+            strip = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
+        import oracle as O
+        O.build()
+        O.set_threads(host_cores())
+        du = dv = 0.0
+        for (z, y, x, uw, vw) in windows:
+            a, b_ = O.window_error(uw, vw, W4K, H4K, ITER, 1234 + rank * pairs + z, y, x, ALPHA, True)
+            du, dv = max(du, a), max(dv, b_)
+        parity = {"max_du": du, "max_dv": dv, "tolerance_px": 1e-3, "ok": bool(du <= 1e-3 and dv <= 1e-3),
+                  "windows": len(windows), "what": f"{K}x{K} windows of pair 0 and pair {pairs - 1} of the timed batch (corner, strip seam, "
+                                                   "corner) vs the oracle on their domains of dependence"}
+        du = dv = 0.0
+        for (k, y, x, uw, vw, f1, f2) in e2e_windows:
+            a, b_ = O.window_error(uw, vw, W4K, H4K, ITER, 0, y, x, ALPHA, True, frames=(f1, f2))
+            du, dv = max(du, a), max(dv, b_)
+        e2e_parity = {"max_du": du, "max_dv": dv, "ok": bool(du <= 1e-3 and dv <= 1e-3), "sampled_equals_full": sampled_ok}
         cpu = cpu_cv = None
         if world == 1 and not args.no_cpu:
             rate, cores, kind, sample, _ = cpu_reference_rate(args.cpu_seconds)
@@ -315,22 +400,33 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic {W4K}x{H4K} gray8 frame pairs, alpha={ALPHA:g}, {ITER} iterations, FULL mode "
-                                   f"(u and v updated), {pairs} pairs per GPU sharded by pair (BASELINE.json configs[3])",
-                       "pairs_per_gpu": pairs, "pairs_per_launch": sub, "temporal_block": T_eff, "math": "fast",
-                       "cache": "working set per step >> 126 MB L2 (no flush needed)"},
+            "config": workload_config(pairs),
+            "engine": {"pairs_per_launch": sub, "temporal_block": T_eff, "math": "fast", "launches_per_step": launches // args.steps},
             "pairs_4k100_per_s": value * 1e6 / (W4K * H4K * ITER),
+            "parity": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": f"k_jacobi_stream<T={T_eff}>", "launch_ms": launch_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "note": "unfused-equivalent bytes (28 B/px-it x T per launch): frac > 1 is the temporal-blocking gain; "
-                                 "ncu dram bytes are in profiles/"},
+                         "fused_min_bytes_per_launch": fused_min_bytes,
+                         "frac_fused_min": fused_min_bytes / (launch_ms * 1e-3) / 1e9 / peak,
+                         "frac_dram": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "traffic_source": traffic_src,
+                         "note": "frac = unfused-equivalent bytes (28 B/px-it x T per launch) / time / peak: > 1 is the temporal-blocking "
+                                 "gain.  frac_fused_min = the 28 B per pixel a launch must move at least; frac_dram = the DRAM bytes ncu "
+                                 "counted for this launch shape (committed capture, scaled per pixel) -- both over the live launch time"},
             "cpu_baseline": cpu,
             "cpu_baseline_opencv": cpu_cv,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W4K * H4K * ep * world,
                     "d2h_bytes_per_step": 8 * W4K * H4K * ep * world, "pairs_per_step": ep * world, "api": "hsflow_run_batch_host",
-                    "host_numa_node_rank0": numa_node,
-                    "result_checksum": result_checksum},
+                    "host_numa_node_rank0": numa_node, "parity": e2e_parity, "gpu_launches_per_step": l_e2e // (1 + max(1, min(args.steps, 3))),
+                    "wire": wire, "wire_bound_value": wire_bound,
+                    "frac_of_wire_bound": (e2e_value / wire_bound) if wire_bound else None,
+                    "sampled": {"value": e2e_sampled, "unit": UNIT, "api": "hsflow_run_pipeline_host(sample_step=4)",
+                                "d2h_bytes_per_step": 8 * (W4K // STEP) * (H4K // STEP) * ep * world,
+                                "frac_of_value": e2e_sampled / value,
+                                "what": "same frames in, only the stride-4 samples of u, v that the reference's consumer reads "
+                                        "(HSOpticalFlowOpenCL.cpp:762-767) come back"}},
+            "strip16k": strip,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -338,6 +434,109 @@ def run_ours(args, rank, world, local_rank):
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def pcie_ceiling(torch, dist, barrier, nbytes=1 << 30, reps=3):
+    """GB/s of plain pinned cudaMemcpyAsync copies, every rank copying at the same time: device -> host alone, host ->
+    device alone, and both directions at once (what the pipeline does).  Min over ranks (max time)."""
+    try:
+        h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        d_in = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        d_out = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        h_in.zero_(); h_out.zero_()
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def run(do_in, do_out):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                if do_out:
+                    with torch.cuda.stream(s1):
+                        h_out.copy_(d_out, non_blocking=True)
+                if do_in:
+                    with torch.cuda.stream(s2):
+                        d_in.copy_(h_in, non_blocking=True)
+            s1.synchronize(); s2.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            if dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return nbytes * reps / float(t.item()) / 1e9
+
+        run(True, True)                               # warm-up
+        out = {"d2h_gbs": run(False, True), "h2d_gbs": run(True, False)}
+        both = run(True, True)
+        out["d2h_gbs_concurrent"] = both              # each direction moved nbytes*reps in that time
+        out["what"] = (f"plain pinned cudaMemcpyAsync of {nbytes >> 20} MiB x {reps} per direction on every rank at the same "
+                       "time, GB/s per GPU (slowest rank); concurrent = both directions in flight")
+        return out
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {ex}"}
+
+
+def strip16k_record(args, torch, dist, rank, world, local_rank, barrier):
+    """BASELINE.json configs[4] as a sub-record of the default line: one 16384 x 16384 pair, 500 iterations, row strips
+    over the `world` GPUs with the fused peer transport (seam rows stored into the neighbours by the iteration kernel,
+    epoch words, stream waits), plus a window check against the oracle done in the run."""
+    import numpy as np
+    import opticalflowhs_b200 as P
+    from opticalflowhs_b200.sharding import StripSolver
+    W = H = 16384
+    N, K = 500, 24
+    stream = torch.cuda.current_stream()
+    eng = P.HSFlow(local_rank)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_params(ALPHA, N, P.STENCIL_CL8, True, args.temporal_block)
+    T = eng.temporal_block
+    transport = "p2p" if world > 1 else "none"
+    solver = StripSolver(eng, W, H, rank, world, T, dist=dist, transport="p2p")
+    solver.load_synth(1234)
+    solver.run(4 * T)
+    barrier()
+    l0 = eng.kernel_launches
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        solver.run(N)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / reps
+    launches = (eng.kernel_launches - l0) // reps
+    # window check: the last K owned rows of rank 0 -- with more than one rank they sit directly on the seam to rank 1
+    # and depend on its rows through every one of the 500 iterations
+    win = None
+    if rank == 0:
+        p = solver.plan
+        y, x = p.hi - K, 73 * (128 - 2 * ((T + 3) // 4 * 4)) - K // 2
+        u, v = eng.read_uv()
+        win = (y, x, u[y - p.a:y - p.a + K, x:x + K].copy(), v[y - p.a:y - p.a + K, x:x + K].copy())
+        del u, v
+    solver.close()
+    eng.close()
+    if rank != 0:
+        return None
+    import oracle as O
+    O.build()
+    O.set_threads(host_cores())
+    y, x, uw, vw = win
+    du, dv = O.window_error(uw, vw, W, H, N, 1234, y, x, ALPHA, True)
+    peak, _ = measured_peaks()
+    value = float(W) * H * N / (ms * 1e-3) / 1e6
+    seams = world - 1
+    return {"workload": f"synthetic {W}x{H} single frame pair, alpha={ALPHA:g}, {N} iterations, FULL mode, row strips over {world} GPU(s) "
+                        "(BASELINE.json configs[4])", "scaling": "strong",
+            "ms_per_500_iterations": ms, "value": value, "unit": UNIT, "transport": transport, "temporal_block": T, "ghost_rows": T,
+            "launches_per_gpu": int(launches),
+            "seam_bytes_per_launch_per_direction": 2 * T * W * 4 if seams else 0,
+            "nvlink_bytes_per_run_all_seams": 2 * seams * (-(-N // T)) * 2 * T * W * 4,
+            "frac_unfused_per_gpu": value * 1e6 * ALG_BYTES_PER_PX_IT / 1e9 / world / peak,
+            "parity": {"max_du": du, "max_dv": dv, "tolerance_px": 1e-3, "ok": bool(du <= 1e-3 and dv <= 1e-3),
+                       "window": {"row": int(y), "col": int(x), "size": K},
+                       "what": "last owned rows of rank 0 (on the seam to rank 1 when N > 1) vs the oracle on the window's domain of dependence"}}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -470,10 +669,11 @@ def main():
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="strip16k: p2p = seam rows pushed by the iteration kernel over NVLink peer memory; nccl = send/recv")
     ap.add_argument("--iterations", type=int, default=0, help="strip16k / sweep1080p: override the iteration count")
-    ap.add_argument("--e2e-pairs", type=int, default=64)
+    ap.add_argument("--e2e-pairs", type=int, default=128)
     ap.add_argument("--temporal-block", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strip", action="store_true", help="pairs4k: skip the strip16k sub-record")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

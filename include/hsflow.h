@@ -100,6 +100,15 @@ int hsflow_set_frames_bgr8(hsflow_t* h, int pair, const uint8_t* f1, const uint8
 int hsflow_set_frames_f32(hsflow_t* h, int pair, const float* f1, const float* f2, size_t pitch);
 /* Same with device pointers (frames already in HBM). */
 int hsflow_set_frames_gray8_dev(hsflow_t* h, int pair, const uint8_t* d_f1, const uint8_t* d_f2, size_t pitch);
+int hsflow_set_frames_bgr8_dev(hsflow_t* h, int pair, const uint8_t* d_f1, const uint8_t* d_f2, size_t pitch);
+/* Zero-copy ingest (cvLoadImage + cvCvtColor, cpp:721-728, without a host bounce): allocates the handle's frame
+ * planes in `frame_format` and returns them, so that an on-GPU decoder (nvJPEG: see hsflow_host_load_pair_jpeg in
+ * libhsflow_host.so) writes its output straight into them; BGR planes are converted to gray inside the derivative
+ * kernel.  Plane layout: [pair][row][row_pitch bytes].  Call again (or any set_frames) after rewriting the planes. */
+enum { HSFLOW_FRAMES_GRAY8 = 0, HSFLOW_FRAMES_BGR8 = 1 };
+int hsflow_map_frames(hsflow_t* h, int frame_format, uint8_t** d_f1, uint8_t** d_f2, size_t* row_pitch, size_t* pair_pitch);
+/* The second-frame planes become the first-frame planes and vice versa (cpp:834 memcpy I2 -> I1 as a pointer swap). */
+int hsflow_swap_frames(hsflow_t* h);
 /* Device-side synthetic frames for benches and large-frame tests (bit-identical to
  * oracle hso_synth_pair): rows [row0, row0+H) of a W x full_height frame, seed0 + pair. */
 int hsflow_synth_frames(hsflow_t* h, int full_height, int row0, uint32_t seed0);
@@ -147,9 +156,18 @@ int hsflow_get_device_frames(hsflow_t* h, uint8_t** d_f1, uint8_t** d_f2, size_t
 /* Drawing predicate of cpp:762-765 on the device: mask[(i/step)*ceil(W/step) + j/step]. */
 int hsflow_dot_mask(hsflow_t* h, int pair, int step, float threshold, uint8_t* mask, int* count); /* sync */
 
+/* Consumer-shaped read-back: u, v of one pair on the stride-`step` grid only -- the reference's only consumer
+ * looks at u[i*w+j], v[i*w+j] for i % 4 == 0, j % 4 == 0 (cpp:762-767).  u_s, v_s: ceil(H/step) x ceil(W/step)
+ * floats each, dense.  8/step^2 bytes per pixel cross PCIe instead of 8. */
+int hsflow_sample_uv(hsflow_t* h, int pair, int step, float* u_s, float* v_s);                    /* sync */
+
 /* ---- pipelined host-to-host batch: H2D, compute and D2H of consecutive pairs overlap --------
  * frames: n_pairs x 2 gray8 images (f1 then f2, densely packed W*H each) in host memory;
- * u_out/v_out: n_pairs x W*H floats.  Pinned host memory gives full PCIe rate. */
+ * u_out/v_out: n_pairs x W*H floats.  Pinned host memory gives full PCIe rate.
+ * These calls RECONFIGURE the handle (geometry w x hgt, an internal number of pair slots) and leave no current field
+ * on the device: hsflow_read_uv / hsflow_dot_mask / hsflow_get_device_uv fail with HSFLOW_EINVAL until the next
+ * hsflow_configure + hsflow_compute.  They return only after every copy from / into the caller's buffers has
+ * finished, on success and on error alike. */
 int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out);
 
 /* ---- frame sequences: replaces the camera loop (cpp:800-842), where every grabbed frame is paired with
@@ -159,6 +177,13 @@ int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w
  * frame crosses PCIe once and is never copied on the device: the second-frame plane of a sub-batch is its
  * first-frame plane shifted by one frame. */
 int hsflow_run_sequence_host(hsflow_t* h, const uint8_t* frames, int n_frames, int w, int hgt, float* u_out, float* v_out);
+/* General form of the two calls above.  frame_format: HSFLOW_FRAMES_GRAY8 (1 byte per pixel) or HSFLOW_FRAMES_BGR8
+ * (3 bytes, cvLoadImage order; gray conversion of cpp:727-728 fused into the derivative kernel).  flags:
+ * HSFLOW_PIPE_SEQUENCE = `frames` holds n_pairs + 1 consecutive frames.  sample_step > 0: u_out / v_out receive the
+ * stride-`step` samples only, n_pairs x ceil(hgt/step) x ceil(w/step) floats each (see hsflow_sample_uv). */
+enum { HSFLOW_PIPE_SEQUENCE = 1 };
+int hsflow_run_pipeline_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, int frame_format, int flags,
+                             int sample_step, float* u_out, float* v_out);
 /* Streaming form for a handle configured with one pair: the current second frame becomes the first
  * (pointer swap in HBM), `frame` is uploaded as the new second frame; then hsflow_compute as usual.
  * The very first frame pushed fills both planes (zero flow). */

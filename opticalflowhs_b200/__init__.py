@@ -7,5 +7,5 @@ oracle/ and has no CPU fallback: without the built library or without a GPU it r
 """
 from .hsflow import (  # noqa: F401
     HSFlow, HSFlowError, lib, library_path,
-    STENCIL_CL8, STENCIL_CV4, MATH_FAST, MATH_EXACT, DERIV_CL, DERIV_CV,
+    STENCIL_CL8, STENCIL_CV4, MATH_FAST, MATH_EXACT, DERIV_CL, DERIV_CV, FRAMES_GRAY8, FRAMES_BGR8, PIPE_SEQUENCE,
 )

@@ -328,6 +328,35 @@ __global__ void k_dot_mask(const float* __restrict__ u, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// k_sample_uv: the fields on the stride-`step` grid the reference's consumer reads (cpp:762-767 looks at u, v
+// only where i % 4 == 0 and j % 4 == 0): out[z][i/step][j/step] = plane[z][i][j].  Results that cross PCIe shrink
+// from 8 B to 8/step^2 B per pixel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sample_uv(const float* __restrict__ u, const float* __restrict__ v, long long row_pitch,
+                                                    long long pair_pitch, int step, float* __restrict__ us, float* __restrict__ vs,
+                                                    int gw, int gh) {
+    const int gj = blockIdx.x * 64 + threadIdx.x, gi = blockIdx.y * 4 + threadIdx.y;
+    if (gj >= gw || gi >= gh) return;
+    const size_t p = (size_t)blockIdx.z * pair_pitch + (size_t)(gi * step) * row_pitch + (size_t)gj * step;
+    const size_t o = ((size_t)blockIdx.z * gh + gi) * gw + gj;
+    us[o] = u[p];
+    vs[o] = v[p];
+}
+
+// k_copy_stopped: EPS mode on the temporally blocked kernel.  A pair that met the criterion keeps its field in the
+// ping-pong buffer it stopped in; at the end of a call the pairs whose buffer is not the final one are copied over.
+__global__ void __launch_bounds__(256) k_copy_stopped(const float4* __restrict__ a, float4* __restrict__ b, long long pair_f4,
+                                                       const int* __restrict__ stop, int final_parity) {
+    const int z = blockIdx.y;
+    const int st = stop[z];
+    if (!st || ((st ^ final_parity) & 1) == 0) return;          // still iterating (field already final) or in place
+    const float4* src = (final_parity ? a : reinterpret_cast<const float4*>(b)) + (size_t)z * pair_f4;
+    float4* dst = (final_parity ? b : const_cast<float4*>(a)) + (size_t)z * pair_f4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pair_f4; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side launchers (called from hsflow_capi.cu)
 // ------------------------------------------------------------------------------------------
 cudaError_t launch_deriv(const DerivArgs& A, int fmt, int pairs, cudaStream_t s) {
@@ -376,6 +405,13 @@ cudaError_t launch_synth(uint8_t* f1, uint8_t* f2, int W, int rows, int full_h, 
                          uint32_t seed0, int pairs, cudaStream_t s) {
     dim3 blk(64, 4), grd((W + 63) / 64, (rows + 3) / 4, pairs);
     k_synth<<<grd, blk, 0, s>>>(f1, f2, W, rows, full_h, row0, rp, pp, seed0);
+    return cudaGetLastError();
+}
+cudaError_t launch_sample_uv(const float* u, const float* v, int W, int H, long long row_pitch, long long pair_pitch, int step,
+                             float* us, float* vs, int pairs, cudaStream_t s) {
+    const int gw = (W + step - 1) / step, gh = (H + step - 1) / step;
+    dim3 blk(64, 4), grd((gw + 63) / 64, (gh + 3) / 4, pairs);
+    k_sample_uv<<<grd, blk, 0, s>>>(u, v, row_pitch, pair_pitch, step, us, vs, gw, gh);
     return cudaGetLastError();
 }
 cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long long pitch, int step, float thr,

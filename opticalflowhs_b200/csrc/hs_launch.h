@@ -93,6 +93,9 @@ cudaError_t launch_eps_check(unsigned* emax, int* stop, double eps, int sweep, i
 cudaError_t launch_eps_settle(int* stop, int total, int pairs, cudaStream_t s);
 cudaError_t launch_synth(uint8_t* f1, uint8_t* f2, int W, int rows, int full_h, int row0, long long rp, long long pp,
                          uint32_t seed0, int pairs, cudaStream_t s);
+// out[z][i/step][j/step] = plane[z][i][j] for both fields (dense [pairs][ceil(H/step)][ceil(W/step)] outputs)
+cudaError_t launch_sample_uv(const float* u, const float* v, int W, int H, long long row_pitch, long long pair_pitch, int step,
+                             float* us, float* vs, int pairs, cudaStream_t s);
 cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long long pitch, int step, float thr,
                             uint8_t* mask, int* count, cudaStream_t s);
 

@@ -52,18 +52,31 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// A lost TMA transaction must fail loudly, never hang the GPU.  The bound is WALL TIME (%globaltimer, 10 s), not a
+// poll count: under a profiler's kernel replay, a sanitizer or heavy co-tenancy a healthy wait can take arbitrarily
+// many polls, but never seconds.  The clock is only read on the slow path (first try_wait failed).
+constexpr uint64_t kMbarTimeoutNs = 10ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok, spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!ok && ++spins > (1u << 22)) __trap();   // a lost TMA transaction must fail loudly, never hang the GPU
-    } while (!ok);
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity))
+        if (globaltimer_ns() - t0 > kMbarTimeoutNs) __trap();
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int x, int pl, int y, int z, uint32_t bar) {
     asm volatile(
@@ -135,6 +148,18 @@ template <int T> struct DefaultCfg {
     using type = StreamCfg<T, RG, NGC, NGUV>;
 };
 
+// Experiment switch (never in the product build): -DHS_EXP_COEF_L2 makes every work unit fetch its coefficient boxes
+// from the same 60 rows of pair 0, so the coefficient stream comes out of L2 instead of HBM.  The results are
+// meaningless; the launch time is an UPPER BOUND for what recomputing a, b, c in-tile from the two 8-bit frames
+// (12 B -> 2 B per pixel and launch) could buy, with the extra arithmetic priced at zero.
+#ifdef HS_EXP_COEF_L2
+#define HS_COEF_Y(y) ((y) % 60)
+#define HS_COEF_Z(z) (0)
+#else
+#define HS_COEF_Y(y) (y)
+#define HS_COEF_Z(z) (z)
+#endif
+
 // ---- the kernel -----------------------------------------------------------------------------------
 #ifndef HS_STREAM_MIN_CTAS
 #define HS_STREAM_MIN_CTAS 1     // experiments: 3 caps the kernel at 168 registers (12 warps per SM)
@@ -195,7 +220,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     auto issue_coef_slot = [&](int g, int slot) {  // lane 0 only: one box = RG rows x {a,b,c} x 128 columns
         const uint32_t bar = cbar_of(slot);
         mbar_expect_tx(bar, (uint32_t)RG * CROW);
-        tma_load_4d(sa32 + (uint32_t)slot * RG * CROW, &tm_c, x0, 0, g * RG, A.z_c0 + z, bar);
+        tma_load_4d(sa32 + (uint32_t)slot * RG * CROW, &tm_c, x0, 0, HS_COEF_Y(g * RG), HS_COEF_Z(A.z_c0 + z), bar);
     };
     auto issue_uv_slot = [&](int g, int slot) {    // lane 0 only: one box = RG rows x {u,v} x 128 columns
         const uint32_t bar = ubar_of(slot);
@@ -452,7 +477,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
                 if ((unsigned)(cy - cymin) <= (unsigned)(ylast - cymin) && ylast >= cymin) {
                     const uint32_t fbar = cbar_of(fslot);
                     mbar_expect_tx(fbar, (uint32_t)RG * CROW);
-                    tma_load_4d(kg[DRET], &tm_c, x0, 0, cy, A.z_c0 + z, fbar);
+                    tma_load_4d(kg[DRET], &tm_c, x0, 0, HS_COEF_Y(cy), HS_COEF_Z(A.z_c0 + z), fbar);
                 }
             }
             uy += RG; cy += RG;

@@ -84,6 +84,8 @@ struct hsflow {
     float *uA = nullptr, *vA = nullptr, *uB = nullptr, *vB = nullptr, *c0 = nullptr, *c1 = nullptr, *c2 = nullptr;
     float* dtmp = nullptr;                         // 3 planes of one pair, for hsflow_read_derivatives
     uint8_t* d_mask = nullptr;
+    float* d_sample = nullptr;                     // hsflow_sample_uv staging
+    size_t sample_cap = 0;
     int* d_count = nullptr;
     size_t mask_cap = 0;
     CUtensorMap tm_uvA[3], tm_uvB[3], tm_c[3];     // [m]: TMA boxes of m + 2 rows (stream_geometry(T).rows_per_box = 2, 3, 4)
@@ -96,6 +98,7 @@ struct hsflow {
     long long launches = 0;
     // peer transport of the row-strip mode: [0] = upper neighbour, [1] = lower neighbour
     StreamWaitValue32Fn wait_value = nullptr;
+    int can_flush = 0;                             // CU_STREAM_WAIT_VALUE_FLUSH supported (cudaDevAttrCanFlushRemoteWrites)
     unsigned* sig = nullptr;                       // device words: [0] epoch from the upper neighbour, [1] from the lower, [2] done counter
     void* peer[2][3] = {};                         // neighbour's uvA, uvB, sig as seen from this device
     int peer_ipc[2] = {};                          // mapped with cudaIpcOpenMemHandle (else same-process raw pointers)
@@ -117,6 +120,13 @@ struct hsflow {
     size_t stage_bytes = 0;
     float *ov_u = nullptr, *ov_v = nullptr;        // output override of the launch run_block issues next
     int uv_dirty = 0;                              // hsflow_write_uv stored a v field since the last zeroing
+    // u = v = 0 at the start of a computation (cpp:331-332) costs no memory traffic on the streaming kernel: its first
+    // launch requests u/v boxes of a pair index beyond the tensor map, which the TMA unit answers with zero fill
+    // without touching HBM (kZeroPair).  zero_pending = "the current buffer is logically zero but was not written":
+    // everything else that looks at the buffer (read-back, single-sweep kernel, halo exchange by the caller)
+    // materialises the zeros first.
+    int zero_pending = 0;
+    int uv_valid = 0;                              // the A/B planes hold a field a caller may read (not after pipelined calls)
     int coef_zero_b = 0;                           // the coefficient planes in memory were written with b = 0
 };
 
@@ -188,6 +198,16 @@ static int make_map(hsflow* h, CUtensorMap* tm, float* base, int planes, int pai
     return HSFLOW_OK;
 }
 
+constexpr int kZeroPair = 1 << 28;                 // pair coordinate outside every tensor map: the box is all zero fill
+
+static int materialize_zero(hsflow* h) {
+    if (!h->zero_pending) return HSFLOW_OK;
+    h->zero_pending = 0;
+    float* uv = h->cur == 0 ? h->uA : h->uB;       // u and v rows share the buffer
+    CK(cudaMemsetAsync(uv, 0, (size_t)h->uv_pp * std::min(h->P, h->cur == 0 ? h->P : h->S) * sizeof(float), h->stream));
+    return HSFLOW_OK;
+}
+
 static void phase_begin(hsflow* h, int ph) { cudaEventRecord(h->ev0[ph], h->stream); }
 static void phase_end(hsflow* h, int ph) { cudaEventRecord(h->ev1[ph], h->stream); h->ev_set[ph] = 1; }
 
@@ -231,6 +251,9 @@ int hsflow_create(int device, hsflow_t** out) {
     e = cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q);
     if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) h->wait_value = (StreamWaitValue32Fn)fn;
     else cudaGetLastError();
+    int flush = 0;
+    if (cudaDeviceGetAttribute(&flush, cudaDevAttrCanFlushRemoteWrites, device) == cudaSuccess) h->can_flush = flush;
+    else cudaGetLastError();
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(HSFLOW_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     h->stream = h->own_stream;
@@ -249,7 +272,7 @@ int hsflow_destroy(hsflow_t* h) {
     free_planes(h);
     cudaFree(h->sig);
     cudaFree(h->d_emax); cudaFree(h->d_stop);
-    cudaFree(h->d_mask); cudaFree(h->d_count);
+    cudaFree(h->d_mask); cudaFree(h->d_count); cudaFree(h->d_sample);
     for (int i = 0; i < 4; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->s_in) cudaStreamDestroy(h->s_in);
@@ -395,6 +418,7 @@ int hsflow_configure(hsflow_t* h, int W, int H, int P) {
     }
     CK(cudaMemsetAsync(h->uA, 0, uvP, h->stream));
     h->cur = 0; h->valid_lo = 0; h->valid_hi = H;
+    h->zero_pending = 0; h->uv_valid = 1;
     return HSFLOW_OK;
 }
 
@@ -410,12 +434,17 @@ static int ensure_frames(hsflow* h, int fmt) {
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2);
     h->f1 = h->f2 = h->fb1 = h->fb2 = nullptr;
+    h->fmt = -1;                                   // no frame planes until both allocations succeeded
+    h->prepared = 0;
     const int bpp = fmt == FMT_GRAY8 ? 1 : (fmt == FMT_BGR8 ? 3 : 4);
     h->f_row_pitch = ((long long)h->W * bpp + 16 + 127) / 128 * 128;   // +16: vector loads may overrun the last pixel
     h->f_pair_pitch = h->f_row_pitch * h->H;
     const size_t bytes = (size_t)h->f_pair_pitch * h->P;
     if (cudaMalloc(&h->f1, bytes) != cudaSuccess || cudaMalloc(&h->f2, bytes) != cudaSuccess) {
         cudaGetLastError();
+        cudaFree(h->f1); cudaFree(h->f2);
+        h->f1 = h->f2 = nullptr;
+        h->f_row_pitch = h->f_pair_pitch = 0;
         return fail(HSFLOW_ENOMEM, "cudaMalloc of frame planes failed");
     }
     CK(cudaMemsetAsync(h->f1, 0, bytes, h->stream));
@@ -452,6 +481,31 @@ int hsflow_set_frames_f32(hsflow_t* h, int pair, const float* f1, const float* f
 }
 int hsflow_set_frames_gray8_dev(hsflow_t* h, int pair, const uint8_t* f1, const uint8_t* f2, size_t pitch) {
     return set_frames(h, FMT_GRAY8, pair, f1, f2, pitch, cudaMemcpyDeviceToDevice);
+}
+int hsflow_set_frames_bgr8_dev(hsflow_t* h, int pair, const uint8_t* f1, const uint8_t* f2, size_t pitch) {
+    return set_frames(h, FMT_BGR8, pair, f1, f2, pitch, cudaMemcpyDeviceToDevice);
+}
+// Zero-copy ingest: the caller (an on-GPU decoder such as nvJPEG) writes frames straight into the handle's planes.
+int hsflow_map_frames(hsflow_t* h, int frame_format, uint8_t** f1, uint8_t** f2, size_t* row_pitch, size_t* pair_pitch) {
+    NEED(h);
+    const int fmt = frame_format == HSFLOW_FRAMES_GRAY8 ? FMT_GRAY8 : (frame_format == HSFLOW_FRAMES_BGR8 ? FMT_BGR8 : -1);
+    if (fmt < 0) return fail(HSFLOW_EINVAL, "frame format must be HSFLOW_FRAMES_GRAY8 or HSFLOW_FRAMES_BGR8");
+    int rc = ensure_frames(h, fmt);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));          // the planes are idle and (when new) zeroed before a foreign stream writes them
+    if (f1) *f1 = h->f1;
+    if (f2) *f2 = h->f2;
+    if (row_pitch) *row_pitch = (size_t)h->f_row_pitch;
+    if (pair_pitch) *pair_pitch = (size_t)h->f_pair_pitch;
+    h->prepared = 0;
+    return HSFLOW_OK;
+}
+int hsflow_swap_frames(hsflow_t* h) {
+    NEED(h);
+    if (!h->f1 || !h->f2) return fail(HSFLOW_EINVAL, "no frame planes");
+    std::swap(h->f1, h->f2);
+    h->prepared = 0;
+    return HSFLOW_OK;
 }
 int hsflow_synth_frames(hsflow_t* h, int full_height, int row0, uint32_t seed0) {
     NEED(h);
@@ -541,7 +595,7 @@ static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T) 
 }
 
 // one launch advancing t iterations for n pairs.  src/dst: 0 = A planes (pair offset pA), 1 = B planes (offset 0)
-static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int out_hi) {
+static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int out_hi, bool zero_in = false) {
     float* uo = src == 0 ? h->uB : h->uA + (size_t)pA * h->uv_pp;
     float* vo = src == 0 ? h->vB : h->vA + (size_t)pA * h->uv_pp;
     if (use_stream_kernel(h, t)) {
@@ -556,7 +610,7 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         A.W = h->W; A.H = h->H; A.out_lo = out_lo; A.out_hi = out_hi;
         const StreamGeom G = stream_geometry(t);
         const int nsx = (h->W + G.valid_w - 1) / G.valid_w;
-        A.z_in0 = src == 0 ? pA : 0;
+        A.z_in0 = zero_in ? kZeroPair : (src == 0 ? pA : 0);
         A.z_c0 = 0;
         A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, nsx, n, t);
         if (h->connected) {                        // fused halo exchange: seam rows go straight into the neighbours' buffers
@@ -576,7 +630,7 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         h->launches++;
         return HSFLOW_OK;
     }
-    if (t != 1) return fail(HSFLOW_EINVAL, "internal: single-sweep kernel advances one iteration per launch");
+    if (t != 1 || zero_in) return fail(HSFLOW_EINVAL, "internal: single-sweep kernel advances one iteration per launch from a real buffer");
     Jacobi1Args A;
     memset(&A, 0, sizeof A);
     A.u_in = src == 0 ? h->uA + (size_t)pA * h->uv_pp : h->uB;
@@ -614,7 +668,7 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
 
 int hsflow_prepare(hsflow_t* h) {
     NEED(h);
-    if (h->P <= 0 || !h->f1) return fail(HSFLOW_EINVAL, "configure and load frames first");
+    if (h->P <= 0 || !h->f1 || !h->f2) return fail(HSFLOW_EINVAL, "configure and load frames first");
     if (h->P > h->S) return fail(HSFLOW_EINVAL, "hsflow_prepare/iterate need pairs <= sub_batch (%d > %d); use hsflow_compute", h->P, h->S);
     CK(cudaSetDevice(h->device));
     phase_begin(h, HSFLOW_PHASE_DERIV);
@@ -624,10 +678,12 @@ int hsflow_prepare(hsflow_t* h) {
     int rc = run_deriv(h, 0, h->P, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp);
     if (rc) return rc;
     h->coef_norm = norm;
+    h->zero_pending = 0;
     if (!h->warm) {                                // cpp:331-332: u, v start at zero for every pair
-        float* uv = h->cur == 0 ? h->uA : h->uB;             // u and v rows share the buffer
-        CK(cudaMemsetAsync(uv, 0, (size_t)h->uv_pp * h->P * sizeof(float), h->stream));
+        h->zero_pending = 1;
+        if (!use_stream_kernel(h, 1)) { if ((rc = materialize_zero(h))) return rc; }
     }
+    h->uv_valid = 1;
     phase_end(h, HSFLOW_PHASE_DERIV);
     h->valid_lo = 0; h->valid_hi = h->H;
     h->sweeps = 0;
@@ -655,13 +711,18 @@ int hsflow_iterate(hsflow_t* h, int n) {
             if ((h->has_peer[0] && h->push_lo[0] < t) || (h->has_peer[1] && h->H - h->push_hi[1] < t) || lo >= hi)
                 return fail(HSFLOW_EINVAL, "strip has fewer ghost rows than the temporal block (%d)", t);
             ++h->epoch;
-            int rc = run_block(h, t, h->cur, 0, h->P, lo, hi);
+            int rc = run_block(h, t, h->cur, 0, h->P, lo, hi, h->zero_pending != 0);
             if (rc) return rc;
+            h->zero_pending = 0;
             h->cur ^= 1;
             h->sweeps += t;
             for (int d = 0; d < 2; ++d)
                 if (h->has_peer[d]) {
-                    CUresult r = h->wait_value((CUstream)h->stream, (CUdeviceptr)(h->sig + d), h->epoch, CU_STREAM_WAIT_VALUE_GEQ);
+                    // FLUSH: the neighbour's seam rows were written over NVLink BEFORE the flag; the next kernel on this
+                    // stream must see them, which the driver only guarantees with the flush flag (where supported --
+                    // otherwise the ordering rests on the writer's __threadfence_system + st.release.sys alone).
+                    CUresult r = h->wait_value((CUstream)h->stream, (CUdeviceptr)(h->sig + d), h->epoch,
+                                               CU_STREAM_WAIT_VALUE_GEQ | (h->can_flush ? CU_STREAM_WAIT_VALUE_FLUSH : 0));
                     if (r != CUDA_SUCCESS) return fail(HSFLOW_ECUDA, "cuStreamWaitValue32 failed with CUresult %d", (int)r);
                 }
             n -= t;
@@ -679,11 +740,13 @@ int hsflow_iterate(hsflow_t* h, int n) {
         if (lo >= hi) return fail(HSFLOW_EINVAL, "ghost rows exhausted: refresh the halo (valid rows [%d,%d), block %d)", h->valid_lo, h->valid_hi, t);
         // the single-sweep path ping-pongs internally; keep the bookkeeping identical for both
         if (use_stream_kernel(h, t)) {
-            int rc = run_block(h, t, h->cur, 0, h->P, lo, hi);
+            int rc = run_block(h, t, h->cur, 0, h->P, lo, hi, h->zero_pending != 0);
             if (rc) return rc;
+            h->zero_pending = 0;
             h->cur ^= 1;
             h->sweeps += t;
         } else {
+            { int rc = materialize_zero(h); if (rc) return rc; }
             for (int k = 0; k < t; ++k) {
                 const int lo1 = h->top_edge ? 0 : h->valid_lo + k + 1;
                 const int hi1 = h->bottom_edge ? h->H : h->valid_hi - k - 1;
@@ -718,15 +781,20 @@ static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nu
     if (rc) return rc;
     h->coef_norm = norm;
     int src = (L % 2 == 0) ? 0 : 1;                // so that the last flip lands in A
-    float* uv = src == 0 ? h->uA + (size_t)p0 * h->uv_pp : h->uB;
-    CK(cudaMemsetAsync(uv, 0, (size_t)h->uv_pp * n * sizeof(float), h->stream));   // cpp:331-332
+    // cpp:331-332 u = v = 0: zero fill by the TMA unit in the first streaming launch, a real memset otherwise
+    bool zero_in = N > 0 && use_stream_kernel(h, std::min(N, T));
+    if (!zero_in) {
+        float* uv = src == 0 ? h->uA + (size_t)p0 * h->uv_pp : h->uB;
+        CK(cudaMemsetAsync(uv, 0, (size_t)h->uv_pp * n * sizeof(float), h->stream));
+    }
     int sweep = 0;
     if (h->eps > 0.0 && (rc = eps_reset(h, p0, n))) return rc;
     for (int left = N; left > 0;) {
         const int t = std::min(left, T);
         if (use_stream_kernel(h, t)) {
             if (left == t) { h->ov_u = fin_u; h->ov_v = fin_v; }
-            rc = run_block(h, t, src, p0, n, 0, h->H);
+            rc = run_block(h, t, src, p0, n, 0, h->H, zero_in);
+            zero_in = false;
             h->ov_u = h->ov_v = nullptr;
             if (rc) return rc;
             src ^= 1;
@@ -747,7 +815,7 @@ static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nu
 
 int hsflow_compute(hsflow_t* h) {
     NEED(h);
-    if (h->P <= 0 || !h->f1) return fail(HSFLOW_EINVAL, "configure and load frames first");
+    if (h->P <= 0 || !h->f1 || !h->f2) return fail(HSFLOW_EINVAL, "configure and load frames first");
     if (h->P <= h->S) {
         int rc = hsflow_prepare(h);
         return rc ? rc : hsflow_iterate(h, h->iterations);
@@ -765,6 +833,7 @@ int hsflow_compute(hsflow_t* h) {
     phase_end(h, HSFLOW_PHASE_ITER);
     h->cur = 0;
     h->prepared = 0;
+    h->zero_pending = 0; h->uv_valid = 1;
     return HSFLOW_OK;
 }
 
@@ -857,6 +926,15 @@ int hsflow_sync(hsflow_t* h) {
     return HSFLOW_OK;
 }
 
+// Readers of the current field: it must exist on the device (the pipelined host calls deliver their results to host
+// memory and leave the planes in an unspecified state) and pending zeros must have been written.
+static int field_ready(hsflow* h) {
+    if (!h->uA) return fail(HSFLOW_EINVAL, "not configured");
+    if (!h->uv_valid)
+        return fail(HSFLOW_EINVAL, "no flow field on the device: hsflow_run_batch_host / hsflow_run_sequence_host deliver their "
+                                   "results to host memory; run hsflow_compute to read fields from the handle");
+    return materialize_zero(h);
+}
 static float* cur_u(hsflow* h) { return h->cur == 0 ? h->uA : h->uB; }
 static float* cur_v(hsflow* h) { return h->cur == 0 ? h->vA : h->vB; }
 
@@ -864,6 +942,7 @@ int hsflow_read_uv(hsflow_t* h, int pair, float* u, float* v, size_t pitch) {
     NEED(h);
     if (pair < 0 || pair >= h->P) return fail(HSFLOW_EINVAL, "pair %d out of range", pair);
     if (h->cur == 1 && pair >= h->S) return fail(HSFLOW_EINVAL, "internal: pair outside scratch planes");
+    { int rc = field_ready(h); if (rc) return rc; }
     const size_t wb = (size_t)h->W * sizeof(float);
     if (pitch == 0) pitch = wb;
     if (pitch < wb) return fail(HSFLOW_EINVAL, "pitch too small");
@@ -878,6 +957,9 @@ int hsflow_read_uv(hsflow_t* h, int pair, float* u, float* v, size_t pitch) {
 int hsflow_write_uv(hsflow_t* h, int pair, const float* u, const float* v, size_t pitch) {
     NEED(h);
     if (pair < 0 || pair >= h->P || (h->cur == 1 && pair >= h->S)) return fail(HSFLOW_EINVAL, "pair %d out of range", pair);
+    if (!h->uA) return fail(HSFLOW_EINVAL, "not configured");
+    { int rc = materialize_zero(h); if (rc) return rc; }
+    h->uv_valid = 1;
     const size_t wb = (size_t)h->W * sizeof(float);
     if (pitch == 0) pitch = wb;
     if (u) CK(cudaMemcpy2DAsync(cur_u(h) + (size_t)pair * h->uv_pp, h->uv_rp * sizeof(float), u, pitch, wb, h->H, cudaMemcpyHostToDevice, h->stream));
@@ -919,7 +1001,7 @@ int hsflow_read_derivatives(hsflow_t* h, int pair, float* Ex, float* Ey, float* 
 
 int hsflow_get_device_uv(hsflow_t* h, float** u, float** v, size_t* row_pitch, size_t* pair_pitch) {
     NEED(h);
-    if (!h->uA) return fail(HSFLOW_EINVAL, "not configured");
+    { int rc = field_ready(h); if (rc) return rc; }
     if (u) *u = cur_u(h);
     if (v) *v = cur_v(h);
     if (row_pitch) *row_pitch = (size_t)h->uv_rp;       // v == u + row_pitch/2: u and v rows interleave
@@ -941,6 +1023,7 @@ int hsflow_dot_mask(hsflow_t* h, int pair, int step, float thr, uint8_t* mask, i
     NEED(h);
     if (pair < 0 || pair >= h->P || step <= 0 || !mask) return fail(HSFLOW_EINVAL, "bad argument");
     if (h->cur == 1 && pair >= h->S) return fail(HSFLOW_EINVAL, "internal: pair outside scratch planes");
+    { int rc = field_ready(h); if (rc) return rc; }
     const int gw = (h->W + step - 1) / step, gh = (h->H + step - 1) / step;
     const size_t need = (size_t)gw * gh;
     if (need > h->mask_cap) {
@@ -960,19 +1043,60 @@ int hsflow_dot_mask(hsflow_t* h, int pair, int step, float thr, uint8_t* mask, i
     return HSFLOW_OK;
 }
 
+int hsflow_sample_uv(hsflow_t* h, int pair, int step, float* u_s, float* v_s) {
+    NEED(h);
+    if (pair < 0 || pair >= h->P || step <= 0 || !u_s || !v_s) return fail(HSFLOW_EINVAL, "bad argument");
+    if (h->cur == 1 && pair >= h->S) return fail(HSFLOW_EINVAL, "internal: pair outside scratch planes");
+    { int rc = field_ready(h); if (rc) return rc; }
+    const int gw = (h->W + step - 1) / step, gh = (h->H + step - 1) / step;
+    const size_t need = 2 * (size_t)gw * gh * sizeof(float);
+    if (need > h->sample_cap) {
+        cudaFree(h->d_sample); h->d_sample = nullptr; h->sample_cap = 0;
+        if (cudaMalloc(&h->d_sample, need) != cudaSuccess) { cudaGetLastError(); return fail(HSFLOW_ENOMEM, "cudaMalloc"); }
+        h->sample_cap = need;
+    }
+    float* ds_u = h->d_sample; float* ds_v = ds_u + (size_t)gw * gh;
+    CK(launch_sample_uv(cur_u(h) + (size_t)pair * h->uv_pp, cur_v(h) + (size_t)pair * h->uv_pp, h->W, h->H, h->uv_rp, h->uv_pp, step,
+                        ds_u, ds_v, 1, h->stream));
+    h->launches++;
+    CK(cudaMemcpyAsync(u_s, ds_u, need / 2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(v_s, ds_v, need / 2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return HSFLOW_OK;
+}
+
 // Three-stage pipeline over sub-batches of B pairs: H2D of sub-batch i+1, compute of i and D2H of i-1 overlap on three
 // streams.  sequence = 0: `frames` holds n_pairs x (f1, f2).  sequence = 1: `frames` holds n_pairs + 1 consecutive
 // frames and pair k = (frame k, frame k+1) -- the camera loop of cpp:800-842, where the second frame of one pair is
 // the first of the next (cpp:834 memcpy I2 -> I1): here each slot holds B + 1 frames in ONE plane and the second-frame
 // pointer is the first-frame pointer plus one frame, so a frame is uploaded once and never copied.
-static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out, int sequence) {
-    if (!frames || !u_out || !v_out || n_pairs <= 0) return fail(HSFLOW_EINVAL, "bad argument");
-    if (!h->top_edge || !h->bottom_edge) return fail(HSFLOW_EINVAL, "not available in strip mode");
+// fmt: gray8 or interleaved BGR8 (cvLoadImage order; the derivative kernel does the cvCvtColor of cpp:727-728).
+// sample_step > 0: u_out / v_out receive the fields on the stride-`step` grid only (what cpp:762-767 reads).
+struct PipeOpts { int fmt, sequence, sample_step; };
+
+static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out, PipeOpts o) {
+    if (!frames || !u_out || !v_out || n_pairs <= 0 || w <= 0 || hgt <= 0) return fail(HSFLOW_EINVAL, "bad argument");
+    if (o.fmt != FMT_GRAY8 && o.fmt != FMT_BGR8) return fail(HSFLOW_EINVAL, "frame format must be gray8 or bgr8");
+    if (o.sample_step < 0) return fail(HSFLOW_EINVAL, "sample_step must be >= 0");
+    if (!h->top_edge || !h->bottom_edge || h->connected) return fail(HSFLOW_EINVAL, "not available in strip mode");
+    CK(cudaSetDevice(h->device));
     const long long px = (long long)w * hgt;
-    int B = (int)std::max<long long>(1, std::min<long long>(16, (32LL << 20) / std::max<long long>(px, 1)));
-    B = std::min(B, n_pairs);
+    const int bpp = o.fmt == FMT_BGR8 ? 3 : 1;
     const int K = 3;                               // sub-batches in flight: H2D | compute | D2H
-    const int slot_pairs = B + (sequence ? 1 : 0); // frame (and result) slots per sub-batch
+    // Pairs per sub-batch: enough pixels that a compute launch runs several waves of work units (units drift apart and
+    // keep HBM and the SMs busy through each other's fill and drain phases): 128 Mi pixels = 16 4K pairs,
+    // at most 64 pairs, and never more than a third of the free device memory for the K slots.
+    int B = (int)std::max<long long>(1, std::min<long long>(64, (128LL << 20) / px));
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+        if (h->uA && h->W == w && h->H == hgt) free_b += (size_t)h->uv_pp * 4 * (h->P + h->S) + (size_t)h->c_pp * 4 * h->S + h->stage_bytes;
+        const double per_pair = (double)px * (K * (8.0 + 2.0 * bpp + 8.0) + 20.0) * 1.1;
+        if (free_b) B = (int)std::max(1.0, std::min((double)B, (double)free_b / 3.0 / per_pair));
+    }
+    if (h->sub_batch > 0) B = std::min(B, h->sub_batch);    // hsflow_set_tuning: tests force several ragged sub-batches
+    B = std::min(B, n_pairs);
+    const int slot_pairs = B + (o.sequence ? 1 : 0); // frame (and result) slots per sub-batch
     if (!(h->W == w && h->H == hgt && h->P == K * slot_pairs && h->S == B)) {
         const int keep = h->sub_batch;
         CK(cudaStreamSynchronize(h->stream));
@@ -982,15 +1106,21 @@ static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, in
         h->sub_batch = keep;
         if (rc) return rc;
     }
-    int rc = ensure_frames(h, FMT_GRAY8);
+    int rc = ensure_frames(h, o.fmt);
     if (rc) return rc;
     if (!h->s_in) { CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)); }
-    // planar staging slots for the read-back: possible when the last block of a sub-batch runs in the streaming kernel
-    // (its output addressing is free) and rows of W floats keep the float4 stores aligned
-    const int T_last = h->iterations > 0 ? (h->iterations % effective_T(h) ? h->iterations % effective_T(h) : effective_T(h)) : 0;
-    const bool planar = (w % 4 == 0) && h->iterations > 0 && use_stream_kernel(h, T_last);
-    const size_t slot_floats = 2 * (size_t)B * px;
-    if (planar && h->stage_bytes < K * slot_floats * sizeof(float)) {
+    // Staging slots for the read-back.  Full fields: the last block of a sub-batch stores PLANAR, densely packed
+    // fields straight into the slot when it runs in the streaming kernel (its output addressing is free) and rows of
+    // W floats keep the float4 stores aligned.  Sampled fields: a gather kernel fills the slot from the A planes.
+    const int T_eff = effective_T(h);
+    const int T_last = h->iterations > 0 ? (h->iterations % T_eff ? h->iterations % T_eff : T_eff) : 0;
+    const int step = o.sample_step;
+    const int gw = step ? (w + step - 1) / step : w, gh = step ? (hgt + step - 1) / step : hgt;
+    const size_t opx = (size_t)gw * gh;            // floats per field and pair that go home
+    const bool planar = !step && (w % 4 == 0) && h->iterations > 0 && use_stream_kernel(h, T_last) && !(h->eps > 0.0);
+    const bool staged = planar || step > 0;
+    const size_t slot_floats = 2 * (size_t)B * opx;
+    if (staged && h->stage_bytes < K * slot_floats * sizeof(float)) {
         CK(cudaStreamSynchronize(h->stream));
         cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0;
         if (cudaMalloc(&h->stage, K * slot_floats * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return fail(HSFLOW_ENOMEM, "cudaMalloc of the read-back staging slots failed"); }
@@ -1005,69 +1135,104 @@ static int run_pipeline(hsflow* h, const uint8_t* frames, int n_pairs, int w, in
     // order the side streams after whatever the handle's stream did so far (allocation memsets)
     CK(cudaEventRecord(ev_comp[0], h->stream));
     CK(cudaStreamWaitEvent(h->s_in, ev_comp[0], 0));
-    const size_t fbytes = (size_t)px, wb = (size_t)w * sizeof(float);
-    // Sub-batch sizes ramp up from one pair and down to one pair again: the read-back is the bottleneck (u, v are 8
-    // bytes per pixel against 2 bytes of frames), so what the call adds to "all results over PCIe" is the time before
-    // the first result can leave (upload + compute of the FIRST sub-batch) and the read-back of the LAST one.
+    CK(cudaStreamWaitEvent(h->s_out, ev_comp[0], 0));
+    const size_t fbytes = (size_t)px * bpp, rowb = (size_t)w * bpp, wb = (size_t)w * sizeof(float);
+    // Sub-batch sizes ramp up from one pair: the first result can only leave after upload + compute of the FIRST
+    // sub-batch.  With full fields the read-back is the bottleneck (8 bytes of u, v per pixel against 1-3 bytes of
+    // frames), so the sizes also ramp down to one pair again: what is left after the last compute is the read-back of
+    // the LAST sub-batch.  Sampled fields are small: no ramp down.
     std::vector<int> sizes;
     {
         std::vector<int> head, tail;
         int left = n_pairs;
-        for (int s = 1; s < B && left > 2 * B; s *= 2) {           // 1, 2, 4, ... at both ends while there is enough work
-            head.push_back(s); tail.push_back(s); left -= 2 * s;
+        const int ends = step ? 1 : 2;
+        for (int s = 1; s < B && left > ends * B; s *= 2) {
+            head.push_back(s); left -= s;
+            if (!step) { tail.push_back(s); left -= s; }
         }
         sizes = head;
         for (; left > 0; left -= B) sizes.push_back(std::min(B, left));
         sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
     }
+    // From here on copies into the caller's buffers may be in flight: every failure leaves through the common exit
+    // below, which drains all three streams before the caller gets its buffers back.
     int status = HSFLOW_OK, first = 0;
-    for (size_t i = 0; i < sizes.size() && status == HSFLOW_OK; first += sizes[i], ++i) {
+#define PK(call)                                                                                                        \
+    do {                                                                                                               \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess) {                                                                                       \
+            status = fail(HSFLOW_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+            goto drain;                                                                                                \
+        }                                                                                                              \
+    } while (0)
+    for (size_t i = 0; i < sizes.size(); first += sizes[i], ++i) {
         const int slot = (int)(i % K), p0 = slot * slot_pairs, n = sizes[i];
-        if (i >= K) CK(cudaStreamWaitEvent(h->s_in, ev_comp[slot], 0));      // frames of the slot were consumed
-        if (sequence) {
+        if (i >= (size_t)K) PK(cudaStreamWaitEvent(h->s_in, ev_comp[slot], 0));      // frames of the slot were consumed
+        if (o.sequence) {
             for (int k = 0; k <= n; ++k)
-                CK(cudaMemcpy2DAsync(h->f1 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, frames + (size_t)(first + k) * fbytes,
-                                     w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
+                PK(cudaMemcpy2DAsync(h->f1 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, frames + (size_t)(first + k) * fbytes,
+                                     rowb, rowb, hgt, cudaMemcpyHostToDevice, h->s_in));
         } else {
             for (int k = 0; k < n; ++k) {
                 const uint8_t* src = frames + (size_t)(first + k) * 2 * fbytes;
-                CK(cudaMemcpy2DAsync(h->f1 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src, w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
-                CK(cudaMemcpy2DAsync(h->f2 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src + fbytes, w, w, hgt, cudaMemcpyHostToDevice, h->s_in));
+                PK(cudaMemcpy2DAsync(h->f1 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src, rowb, rowb, hgt, cudaMemcpyHostToDevice, h->s_in));
+                PK(cudaMemcpy2DAsync(h->f2 + (size_t)(p0 + k) * h->f_pair_pitch, h->f_row_pitch, src + fbytes, rowb, rowb, hgt, cudaMemcpyHostToDevice, h->s_in));
             }
         }
-        CK(cudaEventRecord(ev_in[slot], h->s_in));
-        CK(cudaStreamWaitEvent(h->stream, ev_in[slot], 0));
-        if (i >= K) CK(cudaStreamWaitEvent(h->stream, ev_out[slot], 0));     // u/v of the slot were read back
-        float* su = planar ? h->stage + slot * slot_floats : nullptr;          // U block [n][H][W], then V block
-        float* sv = planar ? su + (size_t)n * px : nullptr;
-        status = sequence ? compute_subbatch(h, p0, n, h->f1, h->f1 + h->f_pair_pitch, su, sv) : compute_subbatch(h, p0, n, nullptr, nullptr, su, sv);
-        if (status) break;
-        CK(cudaEventRecord(ev_comp[slot], h->stream));
-        CK(cudaStreamWaitEvent(h->s_out, ev_comp[slot], 0));
-        if (planar) {
-            CK(cudaMemcpyAsync(u_out + (size_t)first * px, su, (size_t)n * px * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-            CK(cudaMemcpyAsync(v_out + (size_t)first * px, sv, (size_t)n * px * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-        } else for (int k = 0; k < n; ++k) {
-            CK(cudaMemcpy2DAsync(u_out + (size_t)(first + k) * px, wb, h->uA + (size_t)(p0 + k) * h->uv_pp, h->uv_rp * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
-            CK(cudaMemcpy2DAsync(v_out + (size_t)(first + k) * px, wb, h->vA + (size_t)(p0 + k) * h->uv_pp, h->uv_rp * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
+        PK(cudaEventRecord(ev_in[slot], h->s_in));
+        PK(cudaStreamWaitEvent(h->stream, ev_in[slot], 0));
+        if (i >= (size_t)K) PK(cudaStreamWaitEvent(h->stream, ev_out[slot], 0));     // u/v of the slot were read back
+        float* su = staged ? h->stage + slot * slot_floats : nullptr;                  // U block [n][gh][gw], then V block
+        float* sv = staged ? su + (size_t)n * opx : nullptr;
+        status = o.sequence ? compute_subbatch(h, p0, n, h->f1, h->f1 + h->f_pair_pitch, planar ? su : nullptr, planar ? sv : nullptr)
+                            : compute_subbatch(h, p0, n, nullptr, nullptr, planar ? su : nullptr, planar ? sv : nullptr);
+        if (status) goto drain;
+        if (step) {
+            PK(launch_sample_uv(h->uA + (size_t)p0 * h->uv_pp, h->vA + (size_t)p0 * h->uv_pp, w, hgt, h->uv_rp, h->uv_pp, step, su, sv, n, h->stream));
+            h->launches++;
         }
-        CK(cudaEventRecord(ev_out[slot], h->s_out));
+        PK(cudaEventRecord(ev_comp[slot], h->stream));
+        PK(cudaStreamWaitEvent(h->s_out, ev_comp[slot], 0));
+        if (staged) {
+            PK(cudaMemcpyAsync(u_out + (size_t)first * opx, su, (size_t)n * opx * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+            PK(cudaMemcpyAsync(v_out + (size_t)first * opx, sv, (size_t)n * opx * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+        } else for (int k = 0; k < n; ++k) {
+            PK(cudaMemcpy2DAsync(u_out + (size_t)(first + k) * px, wb, h->uA + (size_t)(p0 + k) * h->uv_pp, h->uv_rp * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
+            PK(cudaMemcpy2DAsync(v_out + (size_t)(first + k) * px, wb, h->vA + (size_t)(p0 + k) * h->uv_pp, h->uv_rp * sizeof(float), wb, hgt, cudaMemcpyDeviceToHost, h->s_out));
+        }
+        PK(cudaEventRecord(ev_out[slot], h->s_out));
     }
-    cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->s_out);
-    h->cur = 0; h->prepared = 0;
-    if (status) return status;
+#undef PK
+drain:
+    {
+        // the caller's frames / u_out / v_out are ours until all three streams are idle, error or not
+        const cudaError_t e1 = cudaStreamSynchronize(h->s_in), e2 = cudaStreamSynchronize(h->stream), e3 = cudaStreamSynchronize(h->s_out);
+        // The slots hold the fields of the last K sub-batches (and, with planar staging, not even those): there is no
+        // "current field" a later hsflow_read_uv / hsflow_dot_mask could mean.
+        h->cur = 0; h->prepared = 0; h->zero_pending = 0; h->uv_valid = 0;
+        if (status) return status;
+        const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        if (e != cudaSuccess) return fail(HSFLOW_ECUDA, "pipeline drain: %s", cudaGetErrorString(e));
+    }
     CK(cudaGetLastError());
     return HSFLOW_OK;
 }
 
 int hsflow_run_batch_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, float* u_out, float* v_out) {
     NEED(h);
-    return run_pipeline(h, frames, n_pairs, w, hgt, u_out, v_out, 0);
+    return run_pipeline(h, frames, n_pairs, w, hgt, u_out, v_out, PipeOpts{FMT_GRAY8, 0, 0});
 }
 int hsflow_run_sequence_host(hsflow_t* h, const uint8_t* frames, int n_frames, int w, int hgt, float* u_out, float* v_out) {
     NEED(h);
     if (n_frames < 2) return fail(HSFLOW_EINVAL, "a sequence needs at least two frames");
-    return run_pipeline(h, frames, n_frames - 1, w, hgt, u_out, v_out, 1);
+    return run_pipeline(h, frames, n_frames - 1, w, hgt, u_out, v_out, PipeOpts{FMT_GRAY8, 1, 0});
+}
+int hsflow_run_pipeline_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, int frame_format, int flags,
+                             int sample_step, float* u_out, float* v_out) {
+    NEED(h);
+    if (flags & ~HSFLOW_PIPE_SEQUENCE) return fail(HSFLOW_EINVAL, "unknown pipeline flags 0x%x", flags);
+    const int fmt = frame_format == HSFLOW_FRAMES_GRAY8 ? FMT_GRAY8 : (frame_format == HSFLOW_FRAMES_BGR8 ? FMT_BGR8 : -1);
+    return run_pipeline(h, frames, n_pairs, w, hgt, u_out, v_out, PipeOpts{fmt, (flags & HSFLOW_PIPE_SEQUENCE) ? 1 : 0, sample_step});
 }
 
 // Camera-loop step on the device (cpp:800-842): the second frame of the handle's pair becomes the first one (cpp:834

@@ -7,6 +7,8 @@ import os
 import numpy as np
 
 STENCIL_CL8, STENCIL_CV4 = 0, 1
+FRAMES_GRAY8, FRAMES_BGR8 = 0, 1
+PIPE_SEQUENCE = 1
 MATH_FAST, MATH_EXACT = 0, 1
 DERIV_CL, DERIV_CV = 0, 1
 PHASE_LOAD, PHASE_DERIV, PHASE_ITER, PHASE_READ = 0, 1, 2, 3
@@ -49,6 +51,9 @@ SIGNATURES = {
     "hsflow_set_frames_bgr8": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
     "hsflow_set_frames_f32": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
     "hsflow_set_frames_gray8_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
+    "hsflow_set_frames_bgr8_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
+    "hsflow_map_frames": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "hsflow_swap_frames": (C.c_int, [_P]),
     "hsflow_synth_frames": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32]),
     "hsflow_load_pair_gray8": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_size_t]),
     "hsflow_load_pair_bgr8": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_size_t]),
@@ -67,7 +72,9 @@ SIGNATURES = {
     "hsflow_get_device_uv": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "hsflow_get_device_frames": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "hsflow_dot_mask": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, _P, C.POINTER(C.c_int)]),
+    "hsflow_sample_uv": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "hsflow_run_batch_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "hsflow_run_pipeline_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hsflow_run_sequence_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hsflow_push_frame_gray8": (C.c_int, [_P, _P, C.c_size_t]),
     "hsflow_last_ms": (C.c_float, [_P, C.c_int]),
@@ -242,6 +249,9 @@ class HSFlow:
 
     # ---- results
     def read_uv(self, pair=0):
+        if self.P <= 0:
+            raise HSFlowError(-1, "no flow field on the device (configure + compute first; the pipelined host calls "
+                                  "deliver their results to host memory)")
         u = np.empty((self.H, self.W), np.float32)
         v = np.empty((self.H, self.W), np.float32)
         self._ck(self._L.hsflow_read_uv(self._h, pair, _ptr(u), _ptr(v), 0))
@@ -272,21 +282,66 @@ class HSFlow:
         self._ck(self._L.hsflow_dot_mask(self._h, pair, step, threshold, _ptr(m), C.byref(cnt)))
         return m.astype(bool), cnt.value
 
+    @staticmethod
+    def _host_array(a, dtype, what):
+        """The pipelined calls hand raw pointers to the C side: wrong dtype or a strided view would be read / written
+        as if it were dense, so refuse instead of guessing."""
+        if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags.c_contiguous:
+            raise ValueError(f"{what} must be a C-contiguous numpy array of {np.dtype(dtype).name}")
+        return a
+
+    def _after_pipeline(self, W, H):
+        # the call reconfigured the handle (internal pair slots) and left no current field on the device
+        self.W, self.H, self.P = W, H, 0
+
     def run_batch_host(self, frames, u_out, v_out):
-        """frames: uint8 (n,2,H,W); u_out/v_out: float32 (n,H,W); all C-contiguous (pinned for full rate)."""
-        n, two, H, W = frames.shape
-        assert two == 2 and u_out.shape == (n, H, W) and v_out.shape == (n, H, W)
-        self._ck(self._L.hsflow_run_batch_host(self._h, _ptr(frames), n, W, H, _ptr(u_out), _ptr(v_out)))
-        self.W, self.H = W, H
-        return self
+        """frames: uint8 (n,2,H,W); u_out/v_out: float32 (n,H,W); all C-contiguous (pinned for full rate).
+        Reconfigures the handle; afterwards configure() + compute() are needed before read_uv()."""
+        return self.run_pipeline_host(frames, u_out, v_out)
 
     def run_sequence_host(self, frames, u_out, v_out):
         """frames: uint8 (n+1,H,W) consecutive frames; pair k = (frame k, frame k+1); u_out/v_out: float32 (n,H,W)."""
-        n1, H, W = frames.shape
-        assert n1 >= 2 and u_out.shape == (n1 - 1, H, W) and v_out.shape == (n1 - 1, H, W)
-        self._ck(self._L.hsflow_run_sequence_host(self._h, _ptr(frames), n1, W, H, _ptr(u_out), _ptr(v_out)))
-        self.W, self.H = W, H
+        return self.run_pipeline_host(frames, u_out, v_out, sequence=True)
+
+    def run_pipeline_host(self, frames, u_out, v_out, sequence=False, sample_step=0):
+        """General pipelined call.  frames: uint8 (n,2,H,W[,3]) pairs or, with sequence=True, (n+1,H,W[,3]) consecutive
+        frames; a trailing axis of 3 = interleaved BGR.  sample_step > 0: u_out/v_out are (n, ceil(H/step), ceil(W/step))."""
+        frames = self._host_array(frames, np.uint8, "frames")
+        lead = 1 if sequence else 2
+        if frames.ndim not in (lead + 2, lead + 3) or (frames.ndim == lead + 3 and frames.shape[-1] != 3) or \
+                (not sequence and frames.shape[1] != 2):
+            raise ValueError(f"unsupported frames array {frames.shape}")
+        bgr = frames.ndim == lead + 3
+        n = frames.shape[0] - 1 if sequence else frames.shape[0]
+        H, W = frames.shape[lead], frames.shape[lead + 1]
+        if n < 1:
+            raise ValueError("need at least one frame pair")
+        oshape = (n, -(-H // sample_step), -(-W // sample_step)) if sample_step else (n, H, W)
+        for a, what in ((u_out, "u_out"), (v_out, "v_out")):
+            self._host_array(a, np.float32, what)
+            if a.shape != oshape:
+                raise ValueError(f"{what} must have shape {oshape}, got {a.shape}")
+        rc = self._L.hsflow_run_pipeline_host(self._h, _ptr(frames), n, W, H, FRAMES_BGR8 if bgr else FRAMES_GRAY8,
+                                              PIPE_SEQUENCE if sequence else 0, int(sample_step), _ptr(u_out), _ptr(v_out))
+        self._after_pipeline(W, H)
+        self._ck(rc)
         return self
+
+    def sample_uv(self, pair=0, step=4):
+        """u, v on the stride-`step` grid (what cpp:762-767 reads)."""
+        shape = (-(-self.H // step), -(-self.W // step))
+        u, v = np.empty(shape, np.float32), np.empty(shape, np.float32)
+        self._ck(self._L.hsflow_sample_uv(self._h, pair, step, _ptr(u), _ptr(v)))
+        return u, v
+
+    def map_frames(self, bgr=False):
+        """Device pointers of the handle's frame planes (f1, f2, row_pitch, pair_pitch) for on-GPU decoders."""
+        a, b, rp, pp = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._ck(self._L.hsflow_map_frames(self._h, FRAMES_BGR8 if bgr else FRAMES_GRAY8, C.byref(a), C.byref(b), C.byref(rp), C.byref(pp)))
+        return a.value, b.value, rp.value, pp.value
+
+    def set_frames_bgr_dev(self, d_f1, d_f2, pitch, pair=0):
+        self._ck(self._L.hsflow_set_frames_bgr8_dev(self._h, pair, C.c_void_p(d_f1), C.c_void_p(d_f2), pitch)); return self
 
     def push_frame(self, frame):
         """Camera-loop step: the second frame becomes the first, `frame` (uint8 (H,W)) the new second one."""

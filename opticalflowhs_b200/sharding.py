@@ -198,6 +198,74 @@ class StripSolver:
         return plane[self.plan.lo - self.plan.a:self.plan.hi - self.plan.a]
 
 
+class LocalStripSolver:
+    """Row strips of ONE frame driven by ONE process: `engines[k]` owns strip k (any mix of devices -- eight GPUs of a
+    box, or several handles on one GPU).  Always the fused peer transport: the strips are connected through the
+    same-process branch of hsflow_strip_connect (plain peer access instead of CUDA IPC), every launch stores its seam
+    rows into the neighbours' buffers and the streams wait on each other's epoch words.  No torch.distributed at all.
+
+    All work is asynchronous, so one host thread can feed every strip; launches are issued round-robin in slices of
+    a few temporal blocks so that no strip's stream runs dry (or its launch queue fills up) while the host is still
+    busy with another strip."""
+
+    def __init__(self, engines, width, height, ghost):
+        world = len(engines)
+        self.engines, self.W, self.H = list(engines), width, height
+        self.plans = [StripPlan(height, world, r, ghost) for r in range(world)]
+        for e, p in zip(self.engines, self.plans):
+            e.configure(width, p.rows, 1)
+            e.set_strip(p.is_top, p.is_bottom)
+        self.connected = False
+        if world > 1:
+            handles = [e.strip_export() for e in self.engines]
+            for r, (e, p) in enumerate(zip(self.engines, self.plans)):
+                up, dn = p.push_rows(-1), p.push_rows(+1)
+                e.strip_connect(handles[r - 1] if up else None, up or (0, 0, 0), handles[r + 1] if dn else None, dn or (0, 0, 0))
+            self.connected = True
+
+    def load_synth(self, seed):
+        for e, p in zip(self.engines, self.plans):
+            e.synth_frames(self.H, p.a, seed)
+
+    def load_frames(self, f1, f2):
+        for e, p in zip(self.engines, self.plans):
+            e.set_frames(f1[p.a:p.b], f2[p.a:p.b])
+
+    def run(self, iterations, slice_blocks=8):
+        for e in self.engines:
+            e.prepare()
+        T = max(1, self.engines[0].temporal_block)
+        done = 0
+        while done < iterations:
+            n = min(iterations - done, slice_blocks * T)
+            for e in self.engines:
+                e.iterate(n)
+            done += n
+        return self
+
+    def sync(self):
+        for e in self.engines:
+            e.sync()
+        return self
+
+    def gather_uv(self):
+        """The whole field, assembled on the host from every strip's owned rows (tests; small frames)."""
+        import numpy as np
+        us, vs = [], []
+        for e, p in zip(self.engines, self.plans):
+            u, v = e.read_uv()
+            us.append(u[p.lo - p.a:p.hi - p.a]); vs.append(v[p.lo - p.a:p.hi - p.a])
+        return np.concatenate(us), np.concatenate(vs)
+
+    def close(self):
+        """Peer mappings must go before any strip frees its buffers."""
+        if self.connected:
+            self.sync()
+            for e in self.engines:
+                e.strip_disconnect()
+            self.connected = False
+
+
 def ideal_strip_time_s(width, height, iterations, world, hbm_gbs, bytes_per_px_it=28.0):
     """Lower bound of SURVEY.md 8d: algorithmic bytes / (world x HBM bandwidth)."""
     return width * height * iterations * bytes_per_px_it / (hbm_gbs * 1e9) / world

@@ -226,3 +226,28 @@ def ref_run(g1, g2, alpha, iterations, update_v=True):
     u, v = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
     ref().clref_run(I1, I2, w, h, alpha, iterations, int(update_v), u, v)
     return u, v
+
+
+# ---- large-frame checks without a full CPU run -------------------------------------------
+
+def window_reference(W, H, N, seed, y, x, K, alpha=15.0, update_v=True, frames=None):
+    """u, v of the K x K window at (row y, column x) of a W x H frame after N Jacobi sweeps, computed on the window's
+    domain of dependence only: N sweeps reach N pixels, so a (K + 2N)^2 crop -- clamped where it touches a true image
+    edge, which is then also an edge of the crop -- gives exactly the full-frame values inside the window.
+    frames: (f1, f2) full frames; default = the synthetic pair hso_synth_pair(W, H, seed)."""
+    y0, y1 = max(y - N - 1, 0), min(y + K + N + 1, H)      # one more row/column for the j+1 / i+1 derivative taps
+    x0, x1 = max(x - N - 1, 0), min(x + K + N + 1, W)
+    if frames is None:
+        f1, f2 = synth_pair(W, H, seed=seed, row0=y0, rows=y1 - y0)
+    else:
+        f1, f2 = frames[0][y0:y1], frames[1][y0:y1]
+    uo, vo = run_cl(np.ascontiguousarray(f1[:, x0:x1]), np.ascontiguousarray(f2[:, x0:x1]), alpha, N, update_v)
+    yy, xx = y - y0, x - x0
+    return uo[yy:yy + K, xx:xx + K], vo[yy:yy + K, xx:xx + K]
+
+
+def window_error(u_win, v_win, W, H, N, seed, y, x, alpha=15.0, update_v=True, frames=None):
+    """max |du|, max |dv| of a computed K x K window against window_reference."""
+    K = u_win.shape[0]
+    uo, vo = window_reference(W, H, N, seed, y, x, K, alpha, update_v, frames)
+    return float(np.abs(u_win - uo).max()), float(np.abs(v_win - vo).max())

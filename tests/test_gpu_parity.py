@@ -288,8 +288,9 @@ def test_device_synthetic_frames_equal_oracle_generator(P, oracle):
             assert (bits(x) == bits(y)).all()
 
 
-@pytest.mark.parametrize("W,H,n,math_exact", [(256, 120, 11, False), (232, 64, 41, False), (250, 60, 41, False), (128, 48, 37, True)])
-def test_pipelined_host_batch_equals_per_pair_compute(P, oracle, W, H, n, math_exact):
+@pytest.mark.parametrize("W,H,n,math_exact,sub", [(256, 120, 11, False, 0), (232, 64, 41, False, 4), (250, 60, 41, False, 4),
+                                                  (128, 48, 37, True, 4), (232, 64, 70, False, 16)])
+def test_pipelined_host_batch_equals_per_pair_compute(P, oracle, W, H, n, math_exact, sub):
     """hsflow_run_batch_host against loading every pair separately: one sub-batch; ramped sub-batch sizes with planar
     staging (W % 4 == 0, streaming kernel); the 2-D copy fallback for W % 4 != 0 and for the single-sweep kernel."""
     frames = np.empty((n, 2, H, W), np.uint8)
@@ -299,15 +300,60 @@ def test_pipelined_host_batch_equals_per_pair_compute(P, oracle, W, H, n, math_e
     v = np.empty((n, H, W), np.float32)
     math = P.MATH_EXACT if math_exact else P.MATH_FAST
     with P.HSFlow(0) as e:
-        e.set_math(math).set_params(15.0, 12, P.STENCIL_CL8, True, 4)
+        e.set_math(math).set_params(15.0, 12, P.STENCIL_CL8, True, 4).set_tuning(sub_batch=sub)
         e.run_batch_host(frames, u, v)
+        u[:] = 0; v[:] = 0
         e.run_batch_host(frames, u, v)                  # slots and staging are reused
+        with pytest.raises(P.HSFlowError):              # the call leaves no current field on the device
+            e.read_uv()
+        with pytest.raises(ValueError):                 # raw pointers go to C: dtype and layout are checked
+            e.run_batch_host(frames, u.astype(np.float64), v)
+        with pytest.raises(ValueError):
+            e.run_batch_host(frames[:, :, :, ::2], u, v)
     with P.HSFlow(0) as e:
         e.set_math(math).set_params(15.0, 12, P.STENCIL_CL8, True, 4)
         for k in range(n):
             e.load_pair(frames[k, 0], frames[k, 1]).compute()
             us, vs = e.read_uv()
             assert (bits(u[k]) == bits(us)).all() and (bits(v[k]) == bits(vs)).all(), k
+
+
+@pytest.mark.parametrize("sequence", [False, True])
+def test_pipelined_bgr_frames_and_sampled_fields(P, oracle, sequence):
+    """hsflow_run_pipeline_host with interleaved BGR frames (gray conversion of cpp:727-728 fused into the derivative
+    kernel) and with the consumer-shaped read-back (stride-4 samples, cpp:762-767), against per-pair computes on the
+    gray frames the oracle's fixed-point BGR2GRAY produces; hsflow_sample_uv against read_uv."""
+    W, H, n, N = 236, 70, 23, 14
+    rng = np.random.default_rng(8)
+    nf = n + 1 if sequence else 2 * n
+    bgr = rng.integers(0, 256, (nf, H, W, 3), dtype=np.uint8)
+    gray = np.stack([oracle.bgr2gray(f) for f in bgr])
+    pair = (lambda k: (k, k + 1)) if sequence else (lambda k: (2 * k, 2 * k + 1))
+    want = []
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 4)
+        for k in range(n):
+            a, b = pair(k)
+            e.load_pair(gray[a], gray[b]).compute()
+            want.append(e.read_uv())
+            us, vs = e.sample_uv(0, 4)
+            assert (bits(us) == bits(want[-1][0][::4, ::4])).all() and (bits(vs) == bits(want[-1][1][::4, ::4])).all()
+        us, vs = e.sample_uv(0, 5)
+        assert us.shape == (14, 48) and (bits(us) == bits(want[-1][0][::5, ::5])).all()
+    frames = bgr if sequence else bgr.reshape(n, 2, H, W, 3)
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 4).set_tuning(sub_batch=4)
+        u, v = np.empty((n, H, W), np.float32), np.empty((n, H, W), np.float32)
+        e.run_pipeline_host(frames, u, v, sequence=sequence)
+        for k in range(n):
+            assert (bits(u[k]) == bits(want[k][0])).all() and (bits(v[k]) == bits(want[k][1])).all(), k
+        for step in (4, 3):
+            gh, gw = -(-H // step), -(-W // step)
+            us, vs = np.empty((n, gh, gw), np.float32), np.empty((n, gh, gw), np.float32)
+            e.run_pipeline_host(frames, us, vs, sequence=sequence, sample_step=step)
+            for k in range(n):
+                assert (bits(us[k]) == bits(want[k][0][::step, ::step])).all(), (step, k)
+                assert (bits(vs[k]) == bits(want[k][1][::step, ::step])).all(), (step, k)
 
 
 # ---- strips: host-mediated halo exchange on one GPU ---------------------------------------------------
@@ -328,7 +374,7 @@ def test_frame_sequence_pipeline_and_push_frame_equal_per_pair_compute(P, oracle
             e.load_pair(frames[k], frames[k + 1]).compute()
             want.append(e.read_uv())
     with P.HSFlow(0) as e:
-        e.set_params(15.0, 17, P.STENCIL_CL8, True, 4)
+        e.set_params(15.0, 17, P.STENCIL_CL8, True, 4).set_tuning(sub_batch=4)
         e.run_sequence_host(frames, uo, vo)
         for k in range(n):
             assert (bits(uo[k]) == bits(want[k][0])).all() and (bits(vo[k]) == bits(want[k][1])).all(), k
@@ -379,6 +425,36 @@ def test_row_strips_with_halo_exchange_equal_whole_frame(P, oracle, T, ghost):
     assert (bits(gu) == bits(whole[0])).all() and (bits(gv) == bits(whole[1])).all()
     for e in engs:
         e.close()
+
+
+@pytest.mark.parametrize("T,ghost,N,rows,chunk", [(1, 1, 7, 96, 0), (4, 4, 22, 200, 0), (6, 6, 60, 400, 0), (6, 6, 45, 400, 64),
+                                                  (0, 6, 31, 300, 0), (8, 8, 19, 120, 0), (4, 6, 40, 130, 0)])
+def test_peer_strips_three_handles_on_one_gpu_equal_whole_frame(P, T, ghost, N, rows, chunk):
+    """The fused compute + halo-exchange path (k_jacobi_stream<.., PEER = true>: seam rows stored into the neighbours'
+    buffers, epoch words, cuStreamWaitValue32 between launches) with three strips living in ONE process on ONE GPU,
+    connected through the same-process branch of hsflow_strip_connect.  Tall strips have many row chunks, so the seam
+    chunks run first and the epoch is published while the interior still runs; chunk = 64 keeps every unit counted.
+    Two consecutive runs on the same connection; bit-identical to the whole frame."""
+    from opticalflowhs_b200.sharding import LocalStripSolver
+    W, H, world = 1500, rows * 3 + 9, 3
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, T)
+        e.configure(W, H, 1).synth_frames(0, 0, 4321).compute()
+        whole = e.read_uv()
+    engs = [P.HSFlow(0) for _ in range(world)]
+    try:
+        for e in engs:
+            e.set_params(15.0, N, P.STENCIL_CL8, True, T).set_tuning(chunk_rows=chunk)
+        s = LocalStripSolver(engs, W, H, ghost)
+        s.load_synth(4321)
+        for rep in range(2):
+            s.run(N, slice_blocks=3).sync()
+            u, v = s.gather_uv()
+            assert (bits(u) == bits(whole[0])).all() and (bits(v) == bits(whole[1])).all(), rep
+        s.close()
+    finally:
+        for e in engs:
+            e.close()
 
 
 # ---- OpenCV-mode path -------------------------------------------------------------------------------------
@@ -494,6 +570,49 @@ def test_full_size_frame_windows_against_oracle_crops(P, oracle, W, H, N, T):
         du = np.abs(u[y:y + K, x:x + K] - uo[yy:yy + K, xx:xx + K]).max()
         dv = np.abs(v[y:y + K, x:x + K] - vo[yy:yy + K, xx:xx + K]).max()
         assert du <= TOL_MAX and dv <= TOL_MAX, (y, x, du, dv)
+
+
+def test_bench_geometry_batch_windows_against_oracle_crops(P, oracle):
+    """The timed configuration of bench.py (BASELINE.json configs[3]): 4K pairs, 100 iterations, FULL mode, automatic
+    temporal block (6), MANY pairs in ONE launch (pair coordinate z up to 47, several waves of work units).  Windows
+    of the first, a middle and the last pair -- at corners, on strip seams (multiples of 112 columns) and on row-chunk
+    seams -- against the oracle on their domains of dependence."""
+    W, H, N, K, pairs, seed0 = 3840, 2160, 100, 40, 48, 1234
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 0)
+        e.configure(W, H, pairs).synth_frames(0, 0, seed0)
+        assert e.sub_batch == pairs and e.temporal_block == 6
+        l0 = e.kernel_launches
+        e.compute()
+        assert e.kernel_launches - l0 == 1 + (N + 5) // 6          # one derivative launch + 17 blocks over all pairs
+        fields = {z: e.read_uv(z) for z in (0, pairs // 2 + 1, pairs - 1)}
+    spots = [(0, 0), (H - K, W - K), (H // 2 - K // 2, 9 * 112 - K // 2), (3 * 24 - K // 2, 20 * 112 - K // 2), (1111, 1777)]
+    for z, (u, v) in fields.items():
+        assert np.isfinite(u).all() and np.isfinite(v).all()
+        for (y, x) in spots:
+            du, dv = oracle.window_error(u[y:y + K, x:x + K], v[y:y + K, x:x + K], W, H, N, seed0 + z, y, x)
+            assert du <= TOL_MAX and dv <= TOL_MAX, (z, y, x, du, dv)
+
+
+def test_baseline_config1_bunny_cv_path_as_written(P, oracle, frames):
+    """BASELINE.json configs[0] exactly as the reference runs it (main.cpp:4, 8, 20; OpticalFlowOpenCV.cpp:27-29): the bunny
+    pair, lambda = 0.1, 100 iterations, cvTermCriteria(ITER | EPS, 100, 1e-6), both 3x3 blurs.  The comparator is the
+    restated cvCalcOpticalFlowHS (parity-unpinned: cv210.dll's source is not in the reference tree), so this is the
+    looser cross-check: field within 1e-3 px; in EXACT math the sweep count is equal too."""
+    g1, g2 = frames["bunny_1"], frames["bunny_2"]
+    uo, vo, it = oracle.run_cv(g1, g2, 0.1, 100, eps=1e-6)
+    for math in (P.MATH_EXACT, P.MATH_FAST):
+        with P.HSFlow(0) as e:
+            e.set_math(math).set_deriv(P.DERIV_CV).set_params(0.0, 100, P.STENCIL_CV4, True, 0).set_lambda(0.1).set_epsilon(1e-6)
+            e.load_pair(g1, g2).compute()
+            u, v = e.read_uv()
+            done = e.iterations_done(0)
+        assert np.abs(u - uo).max() <= TOL_MAX and np.abs(v - vo).max() <= TOL_MAX, math
+        assert epe_diff(u, v, uo, vo) <= TOL_EPE
+        if math == P.MATH_EXACT:
+            assert done == it
+        else:
+            assert abs(done - it) <= 1 or done == it == 100
 
 
 def test_16k_frame_500_iterations_windows_against_oracle_crops(P, oracle):

@@ -6,7 +6,7 @@ import oracle as O
 import opticalflowhs_b200 as P
 
 def bits(a): return np.ascontiguousarray(a, np.float32).view(np.uint32)
-fr = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "frames.npz")))
+fr = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "frames.npz")))
 g1, g2 = fr["bunny_1"], fr["bunny_2"]
 e = P.HSFlow(0)
 e.load_pair(g1, g2)
