@@ -79,9 +79,12 @@ int hsflow_set_tuning(hsflow_t* h, int chunk_rows, int warps_per_cta, int sub_ba
 int hsflow_set_warm_start(hsflow_t* h, int keep_uv);      /* use_previous (cv.h:481-483)        */
 /* The EPS half of cvTermCriteria(CV_TERMCRIT_ITER | CV_TERMCRIT_EPS, it, 1e-6) (OpticalFlowOpenCV.cpp:29,
  * 94): every pair stops after the first sweep whose max |new - old| over u and v is < eps, or after
- * `iterations` sweeps.  eps <= 0 (default) = ITER only, as runCLKernels (cpp:750-751).  While eps > 0 the
- * iteration runs one fused sweep per launch with an in-kernel max-norm reduction and a device-side
- * stop word per pair (no host round trip); not available in strip mode. */
+ * `iterations` sweeps.  eps <= 0 (default) = ITER only, as runCLKernels (cpp:750-751).  The decision is taken
+ * on the device (max-norm reduction inside the iteration kernel, a stop word per pair): no host round trip, the
+ * launch sequence stays asynchronous.  FAST math keeps the temporally blocked kernel: blocks of up to 4 sweeps that
+ * track the max-norm of every sweep, and a pair that met the criterion inside a block is replayed from the block's
+ * input for exactly that many sweeps -- sweep count and field are bit-identical to checking after every sweep.
+ * EXACT math runs one sweep per launch.  Not available in strip mode. */
 int hsflow_set_epsilon(hsflow_t* h, double eps);
 /* 0 = auto; 1 = single-sweep kernel only (one launch per iteration); 2 = streaming kernel even for T = 1 */
 int hsflow_set_kernel(hsflow_t* h, int which);

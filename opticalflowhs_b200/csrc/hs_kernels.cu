@@ -10,6 +10,8 @@
 //   k_dot_mask  drawing predicate of cpp:762-765
 // All kernels are HBM-bound byte/float streaming: vectorised (float4 / uchar4) coalesced access,
 // one warp per 128-column strip, no tensor cores by design.
+#include <algorithm>
+
 #include "hs_common.cuh"
 #include "hs_launch.h"
 
@@ -343,17 +345,23 @@ __global__ void __launch_bounds__(256) k_sample_uv(const float* __restrict__ u, 
     vs[o] = v[p];
 }
 
-// k_copy_stopped: EPS mode on the temporally blocked kernel.  A pair that met the criterion keeps its field in the
-// ping-pong buffer it stopped in; at the end of a call the pairs whose buffer is not the final one are copied over.
-__global__ void __launch_bounds__(256) k_copy_stopped(const float4* __restrict__ a, float4* __restrict__ b, long long pair_f4,
+// k_copy_stopped / k_relabel_stopped: EPS mode on the temporally blocked kernel.  A pair that met the criterion keeps
+// its field in the ping-pong buffer it stopped in (low bit of its stop word); at the end of a call the pairs whose
+// buffer is not the final one are copied over, then their words are re-labelled (a second launch: every block of the
+// copy reads the old label).
+__global__ void __launch_bounds__(256) k_copy_stopped(float4* __restrict__ a, float4* __restrict__ b, long long pair_f4,
                                                        const int* __restrict__ stop, int final_parity) {
     const int z = blockIdx.y;
     const int st = stop[z];
-    if (!st || ((st ^ final_parity) & 1) == 0) return;          // still iterating (field already final) or in place
-    const float4* src = (final_parity ? a : reinterpret_cast<const float4*>(b)) + (size_t)z * pair_f4;
-    float4* dst = (final_parity ? b : const_cast<float4*>(a)) + (size_t)z * pair_f4;
+    if (!st || ((st ^ final_parity) & 1) == 0) return;          // still iterating (its field is where the blocks left it) or in place
+    const float4* src = (final_parity ? a : b) + (size_t)z * pair_f4;
+    float4* dst = (final_parity ? b : a) + (size_t)z * pair_f4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pair_f4; i += (long long)gridDim.x * blockDim.x)
         dst[i] = src[i];
+}
+__global__ void k_relabel_stopped(int* stop, int final_parity, int pairs) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z < pairs && stop[z]) stop[z] = (stop[z] & ~1) | (final_parity & 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -412,6 +420,14 @@ cudaError_t launch_sample_uv(const float* u, const float* v, int W, int H, long 
     const int gw = (W + step - 1) / step, gh = (H + step - 1) / step;
     dim3 blk(64, 4), grd((gw + 63) / 64, (gh + 3) / 4, pairs);
     k_sample_uv<<<grd, blk, 0, s>>>(u, v, row_pitch, pair_pitch, step, us, vs, gw, gh);
+    return cudaGetLastError();
+}
+cudaError_t launch_copy_stopped(float* a, float* b, long long pair_floats, int* stop, int final_parity, int pairs, cudaStream_t s) {
+    if (pairs <= 0) return cudaSuccess;
+    const long long f4 = pair_floats / 4;                       // plane pitches are multiples of 32 floats
+    dim3 grd((unsigned)std::min<long long>(1024, (f4 + 255) / 256), pairs);
+    k_copy_stopped<<<grd, 256, 0, s>>>(reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), f4, stop, final_parity);
+    k_relabel_stopped<<<(pairs + 127) / 128, 128, 0, s>>>(stop, final_parity, pairs);
     return cudaGetLastError();
 }
 cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long long pitch, int step, float thr,

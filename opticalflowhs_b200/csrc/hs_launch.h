@@ -76,6 +76,22 @@ struct StreamArgs {
     unsigned* flag_up;          // word in the upper / lower neighbour's memory that receives `epoch`
     unsigned* flag_dn;
     unsigned epoch;
+    // EPS criterion on the temporally blocked kernel (TRACK instantiation; cvTermCriteria(ITER | EPS), cv.cpp:29).
+    // A block of trk_t <= T sweeps runs as TWO launches over the same source and destination buffers:
+    //   main   (trk_mode 0): pairs that are still iterating run all trk_t sweeps; every stage S reduces
+    //          max |x(S+1) - x(S)| over the pixels the unit owns into emax[pair][S] (atomicMax on the float bits);
+    //   replay (trk_mode 1): a pair whose FIRST stage s with emax[pair][s] < eps exists should have stopped after
+    //          s + 1 sweeps: its units run again from the (still intact) source buffer with the stages >= s + 1
+    //          passing their input through, overwrite the destination with the field after exactly s + 1 sweeps and
+    //          record stop[pair] = ((trk_base + s + 1) << 1) | trk_dst_parity.  Units of every other pair exit at once.
+    // No host round trip: the launch sequence stays asynchronous.  Bit-identical in sweep count and field to the
+    // single-sweep kernel with its per-sweep check (k_jacobi1<.., TRACK>).
+    int* stop;                  // [pairs] 0 = still iterating, else (sweeps executed << 1) | buffer that holds the field (0 = A planes, 1 = B planes)
+    unsigned* emax;             // [pairs][kMaxT], this block's bank (zero on entry of the main launch)
+    unsigned* emax_next;        // the other bank: zeroed by the replay launch for the next block
+    int trk_mode, trk_t, trk_base, trk_dst_parity;
+    int z_trk0;                 // first pair's index into stop / emax
+    double eps;
 };
 
 struct StreamGeom {             // filled by stream_geometry()
@@ -110,5 +126,12 @@ int stream_warps_per_sm(int T, int stencil);   // resident warps (= CTAs) per SM
 // stream_geometry(T).rows_per_box rows.  One warp per CTA.
 cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tm_uv, const CUtensorMap& tm_c,
                                  StreamArgs A, int pairs, cudaStream_t s);
+// EPS mode: the TRACK instantiation exists for one depth only; shorter (tail) blocks run on it with trk_t < kTrackT
+constexpr int kTrackT = 4;
+cudaError_t launch_jacobi_stream_track(int stencil, const CUtensorMap& tm_uv, const CUtensorMap& tm_c, StreamArgs A, int pairs,
+                                       cudaStream_t s);
+// end of a call in EPS mode: pairs that stopped in the other ping-pong buffer are copied into the final one
+// (a, b: the A-plane and B-plane blocks of the n pairs; final_parity: which of them holds the result), then re-labelled
+cudaError_t launch_copy_stopped(float* a, float* b, long long pair_floats, int* stop, int final_parity, int pairs, cudaStream_t s);
 
 }  // namespace hs

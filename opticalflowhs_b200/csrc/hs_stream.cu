@@ -13,6 +13,8 @@ namespace hs {
 HS_DECL(1) HS_DECL(2) HS_DECL(3) HS_DECL(4) HS_DECL(5) HS_DECL(6) HS_DECL(7) HS_DECL(8)
 #undef HS_DECL
 
+cudaError_t stream_launch_track(int, const CUtensorMap&, const CUtensorMap&, const StreamArgs&, cudaStream_t);   // hs_stream_inst.cu, T = kTrackT
+
 template <int T> static StreamGeom geom_of() {
     using C = typename DefaultCfg<T>::type;
     return StreamGeom{C::HL, C::VALIDW, C::SMEM_WARP, kMaxT, C::RG};
@@ -43,6 +45,21 @@ int stream_warps_per_sm(int T, int stencil) {
         case 5: return stream_occ_T5(stencil); case 6: return stream_occ_T6(stencil);
         case 7: return stream_occ_T7(stencil); default: return stream_occ_T8(stencil);
     }
+}
+
+cudaError_t launch_jacobi_stream_track(int stencil, const CUtensorMap& tuv, const CUtensorMap& tc, StreamArgs A, int pairs,
+                                       cudaStream_t s) {
+    const StreamGeom G = stream_geometry(kTrackT);
+    const int rows = A.out_hi - A.out_lo;
+    if (rows <= 0 || pairs <= 0) return cudaSuccess;
+    if (A.done_counter != nullptr || A.stop == nullptr || A.emax == nullptr || A.emax_next == nullptr || A.trk_t < 1 || A.trk_t > kTrackT)
+        return cudaErrorInvalidValue;
+    A.nsx = (A.W + G.valid_w - 1) / G.valid_w;
+    A.ncy = (rows + A.chunk_rows - 1) / A.chunk_rows;
+    A.total_units = (long long)A.nsx * A.ncy * pairs;
+    A.seam_first = 0;
+    A.signal_units = A.total_units;
+    return stream_launch_track(stencil, tuv, tc, A, s);
 }
 
 cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tuv, const CUtensorMap& tc, StreamArgs A, int pairs,

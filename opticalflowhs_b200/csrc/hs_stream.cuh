@@ -164,7 +164,7 @@ template <int T> struct DefaultCfg {
 #ifndef HS_STREAM_MIN_CTAS
 #define HS_STREAM_MIN_CTAS 1     // experiments: 3 caps the kernel at 168 registers (12 warps per SM)
 #endif
-template <int T, int ST, bool PEER>
+template <int T, int ST, bool PEER, bool TRACK = false>
 __global__ void __launch_bounds__(32, HS_STREAM_MIN_CTAS)
 k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant__ CUtensorMap tm_c, const StreamArgs A) {
     using C = typename DefaultCfg<T>::type;
@@ -188,6 +188,24 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     const int z = (int)(tt / A.ncy);
     if (PEER && A.seam_first && A.ncy > 2) cy = cy == 0 ? 0 : (cy == 1 ? A.ncy - 1 : cy - 1);   // seam chunks run first
     const bool counted = !PEER || !A.seam_first || cy == 0 || cy == A.ncy - 1;
+    // EPS criterion (StreamArgs::stop ... eps): `lim` = stages that really iterate; the others pass their input through
+    int lim = T;
+    const int zt = TRACK ? A.z_trk0 + z : 0;
+    if constexpr (TRACK) {
+        const int st = A.stop[zt];
+        if (A.trk_mode == 0) {
+            if (st) return;                        // this pair met the criterion in an earlier block
+            lim = A.trk_t;
+        } else {
+            if (sx == 0 && cy == 0 && lane < kMaxT) A.emax_next[zt * kMaxT + lane] = 0u;
+            if (st && (st >> 1) <= A.trk_base) return;
+            int s = 0;                             // first sweep of the block whose max-norm fell below eps
+            while (s < A.trk_t && !((double)__uint_as_float(A.emax[zt * kMaxT + s]) < A.eps)) ++s;
+            if (s == A.trk_t) return;              // none: the main launch's result stands
+            lim = s + 1;
+            if (lane == 0) A.stop[zt] = ((A.trk_base + lim) << 1) | A.trk_dst_parity;   // every unit of the pair writes the same word
+        }
+    }
     const int W = A.W, H = A.H;
     const int R0 = A.out_lo + cy * A.chunk_rows;
     const int R1 = min(R0 + A.chunk_rows, A.out_hi);
@@ -260,6 +278,31 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         for (int j = 0; j < 4; ++j) { p[s][j] = 0ull; g[s][j] = 0ull; }
 
     const bool lane_out = (lane >= C::HL / 4) && (lane < 32 - C::HL / 4) && (col0 < W);
+    // TRACK: what each stage received one tick ago (= the old value of the row it puts out now) and its running
+    // max |new - old| over the pixels this unit owns (rows [R0, R1), the strip's valid columns, columns < W)
+    constexpr int TS = TRACK ? T : 1;
+    float pu[TS][4], pv[TS][4], em[TS];
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+        em[s] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { pu[s][j] = 0.f; pv[s][j] = 0.f; }
+    }
+    const int wj = min(max(W - col0, 0), 4);       // this lane's columns inside the image
+    auto pass_through = [&](const int S, float (&cu)[4], float (&cv)[4]) {   // stage S >= lim: out = previous input
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float tu = pu[S][j], tv = pv[S][j];
+            pu[S][j] = cu[j]; pv[S][j] = cv[j];
+            cu[j] = tu; cv[j] = tv;
+        }
+    };
+    auto track_delta = [&](const int S, const float (&cu)[4], const float (&cv)[4], const bool all_cols) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (all_cols || j < wj)
+                em[S] = fmaxf(em[S], fmaxf(fabsf(__fsub_rn(cu[j], pu[S][j])), fabsf(__fsub_rn(cv[j], pv[S][j]))));
+    };
     float* uo = A.u_out + (size_t)z * A.out_pair_pitch + col0;
     float* vo = A.v_out + (size_t)z * A.out_pair_pitch + col0;
 
@@ -295,9 +338,15 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
 
     // one stage-row in steady state: time step S of one row (cu, cv) -> time step S+1 of the row
     // above it, written back into cu, cv.  ka, kb, kc = this lane's coefficients of that row.
-    auto stage_row = [&](auto edge_tag, auto s_tag, float (&cu)[4], float (&cv)[4], const float4& ka, const float4& kb, const float4& kc) {
+    auto stage_row = [&](auto edge_tag, auto s_tag, float (&cu)[4], float (&cv)[4], const float4& ka, const float4& kb, const float4& kc,
+                         const bool own) {
         constexpr bool EDGE = decltype(edge_tag)::value;
         constexpr int S = decltype(s_tag)::value;
+        [[maybe_unused]] float iu[4], iv[4];
+        if constexpr (TRACK) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { iu[j] = cu[j]; iv[j] = cv[j]; }
+        }
         if (EDGE && wmis) { sanitize_right(cu, col0, W); sanitize_right(cv, col0, W); }
         float lu = __shfl_up_sync(kFull, cu[3], 1), ru = __shfl_down_sync(kFull, cu[0], 1);
         float lv = __shfl_up_sync(kFull, cv[3], 1), rv = __shfl_down_sync(kFull, cv[0], 1);
@@ -315,6 +364,11 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             p[S][2 + j] = pOf2<ST>(g[S][2 + j], hv[j]); g[S][2 + j] = Gv;
         }
         update_rows(ub, vb, ka, kb, kc, cu, cv);
+        if constexpr (TRACK) {
+            if (own) track_delta(S, cu, cv, !EDGE);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { pu[S][j] = iu[j]; pv[S][j] = iv[j]; }
+        }
     };
 
     // ---- generic tick: pipeline fill, bottom-edge drain, tiny frames (runtime predicates) ----------
@@ -342,6 +396,23 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             if (rho < rs || rho > H) have = false;
             else if (rho == H) { virt = true; have = true; }   // row H == row H-1 (clamp)
             if (!have) continue;
+            if constexpr (TRACK) {
+                if (S >= lim) {                    // pass-through stage
+                    if (virt) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { cu[j] = pu[S][j]; cv[j] = pv[S][j]; }
+                    } else {
+                        pass_through(S, cu, cv);
+                        if (rho == rs) have = false;   // first row of the stage: nothing to put out yet
+                    }
+                    continue;
+                }
+            }
+            [[maybe_unused]] float iu[4], iv[4];
+            if constexpr (TRACK) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { iu[j] = cu[j]; iv[j] = cv[j]; }
+            }
             f32x2 ub[2], vb[2];
             if (virt) {
 #pragma unroll
@@ -365,6 +436,10 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
                         p[S][j] = pOf2<ST>(Gu, hu[j]); g[S][j] = Gu;
                         p[S][2 + j] = pOf2<ST>(Gv, hv[j]); g[S][2 + j] = Gv;
                     }
+                    if constexpr (TRACK) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { pu[S][j] = iu[j]; pv[S][j] = iv[j]; }
+                    }
                     have = false;
                     continue;
                 }
@@ -383,6 +458,13 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             const float4 kb = *reinterpret_cast<const float4*>(sa_l + ROWB + q);
             const float4 kc = *reinterpret_cast<const float4*>(sa_l + 2 * ROWB + q);
             update_rows(ub, vb, ka, kb, kc, cu, cv);
+            if constexpr (TRACK) {                 // time step S+1 of row rho-1 against its time step S
+                if (lane_out && rho - 1 >= R0 && rho - 1 < R1) track_delta(S, cu, cv, false);
+                if (!virt) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { pu[S][j] = iu[j]; pv[S][j] = iv[j]; }
+                }
+            }
         }
         const int ro = r - T;
         if (have && lane_out && ro >= R0 && ro < R1) {
@@ -451,8 +533,12 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
                     constexpr int REL = J - S - 1;
                     constexpr int K = REL >= 0 ? 0 : (-REL + RG - 1) / RG;
                     constexpr int OFF = (REL + K * RG) * CROW;
+                    if constexpr (TRACK) {
+                        if (S >= lim) { pass_through(S, cu, cv); return; }
+                    }
                     const float4 ka = lds128<OFF>(kg[K]), kb = lds128<OFF + ROWB>(kg[K]), kc = lds128<OFF + 2 * ROWB>(kg[K]);
-                    stage_row(edge_tag, s_tag, cu, cv, ka, kb, kc);
+                    // the row this stage puts out is (T - S - 1) rows below the row the tick stores
+                    stage_row(edge_tag, s_tag, cu, cv, ka, kb, kc, TRACK && (orow + (unsigned)(J + T - S - 1) < out_rows));
                 };
                 [&]<int... S>(std::integer_sequence<int, S...>) {
                     (stage(std::integral_constant<int, S>{}), ...);
@@ -509,6 +595,18 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             r = steady(std::false_type{}, r, st_end);
         }
         gen_end = last_tick + 1;                                 // bottom edge / remainder: generic ticks
+    }
+
+    if constexpr (TRACK) {
+        if (A.trk_mode == 0) {                     // main launch: this unit's share of the per-stage max-norms
+#pragma unroll
+            for (int s = 0; s < TS; ++s) {
+                float m = em[s];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, d));
+                if (lane == 0 && s < lim && m > 0.f) atomicMax(A.emax + zt * kMaxT + s, __float_as_uint(m));
+            }
+        }
     }
 
     // Halo-exchange signal: every counted unit (all of them, or just the two seam chunks -- StreamArgs::seam_first)

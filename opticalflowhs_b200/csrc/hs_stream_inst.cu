@@ -40,6 +40,27 @@ cudaError_t HS_FN(stream_launch_T)(int st, bool peer, const CUtensorMap& tuv, co
     return peer ? launch_one<ST_CV4, true>(tuv, tc, A, s) : launch_one<ST_CV4, false>(tuv, tc, A, s);
 }
 
+#if HS_STREAM_T == 4
+// The EPS-criterion (TRACK) instantiation exists for this depth only (kTrackT).
+static_assert(kTrackT == 4, "instantiate k_jacobi_stream<kTrackT, .., TRACK = true> in the matching object");
+template <int ST> static cudaError_t launch_track_one(const CUtensorMap& tuv, const CUtensorMap& tc, const StreamArgs& A, cudaStream_t s) {
+    using C = typename DefaultCfg<kT>::type;
+    static bool prepared = false;                  // one attribute call per instantiation and process
+    if (!prepared) {
+        cudaError_t e = cudaFuncSetAttribute(k_jacobi_stream<kT, ST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        prepared = true;
+    }
+    if (A.total_units <= 0) return cudaSuccess;
+    if (A.total_units > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    k_jacobi_stream<kT, ST, false, true><<<(unsigned)A.total_units, 32, C::SMEM_WARP, s>>>(tuv, tc, A);
+    return cudaGetLastError();
+}
+cudaError_t stream_launch_track(int st, const CUtensorMap& tuv, const CUtensorMap& tc, const StreamArgs& A, cudaStream_t s) {
+    return st == ST_CL8 ? launch_track_one<ST_CL8>(tuv, tc, A, s) : launch_track_one<ST_CV4>(tuv, tc, A, s);
+}
+#endif
+
 int HS_FN(stream_occ_T)(int st) {
     using C = typename DefaultCfg<kT>::type;
     int n = 0;

@@ -113,6 +113,7 @@ struct hsflow {
     int eps_cap = 0;                               // pairs the two arrays hold
     int sweeps = 0;                                // sweeps since hsflow_prepare (hsflow_iterate path)
     int ec_on = 0, ec_sweep = 0, ec_total = 0, ec_off = 0;   // tracking context of the sweep run_block launches next
+    int ec_blk = 0;                                // EPS on the streaming kernel: blocks launched since the words were reset (emax bank = parity)
     // host pipeline: the last launch of a sub-batch stores PLANAR, densely packed fields ([pair][H][W] of u, then of v)
     // into a staging slot, so that the read-back is two contiguous copies (56.9 GB/s over PCIe against 51.8 GB/s for
     // the row-by-row de-interleaving 2-D copy out of the u|v buffer, tools/microbench/d2h_bench.cu)
@@ -173,15 +174,19 @@ static int auto_T(const hsflow* h) {
 static bool literal_on_stream(const hsflow* h) {
     return !h->update_v && h->math == HSFLOW_MATH_FAST && !h->warm && !h->uv_dirty;
 }
-static int effective_T(const hsflow* h) {
-    if (h->math == HSFLOW_MATH_EXACT || (!h->update_v && !literal_on_stream(h)) || h->kernel_sel == 1 || h->eps > 0.0) return 1;
-    int T = h->tblock > 0 ? h->tblock : auto_T(h);
-    return std::min(T, kMaxT);
-}
 static bool use_stream_kernel(const hsflow* h, int t) {
-    if (h->math == HSFLOW_MATH_EXACT || (!h->update_v && !literal_on_stream(h)) || h->kernel_sel == 1 || h->eps > 0.0) return false;
+    if (h->math == HSFLOW_MATH_EXACT || (!h->update_v && !literal_on_stream(h)) || h->kernel_sel == 1) return false;
     (void)t;                                       // also for a single iteration: at T = 1 the TMA-fed streaming kernel
     return true;                                   // moves 5.3 TB/s where k_jacobi1 moves 4.6-4.8 (tools/gpu_perf_probe.py)
+}
+// EPS criterion (hsflow_set_epsilon) on the temporally blocked kernel: the TRACK instantiation (StreamArgs::stop ...),
+// blocks of up to kTrackT sweeps, each a main launch + a replay launch.  EXACT math keeps the single-sweep kernel.
+static bool eps_on_stream(const hsflow* h) { return h->eps > 0.0 && use_stream_kernel(h, 1); }
+static int effective_T(const hsflow* h) {
+    if (!use_stream_kernel(h, 1)) return 1;
+    if (h->eps > 0.0) return h->tblock > 0 ? std::min(h->tblock, kTrackT) : kTrackT;
+    int T = h->tblock > 0 ? h->tblock : auto_T(h);
+    return std::min(T, kMaxT);
 }
 
 // 4-D map {W, planes, H, pairs} over a row-interleaved buffer; box = 128 columns x all planes x box_rows rows
@@ -349,15 +354,19 @@ static int eps_reset(hsflow* h, int off, int n) {
     if (h->eps_cap < h->P) {
         cudaFree(h->d_emax); cudaFree(h->d_stop);
         h->d_emax = nullptr; h->d_stop = nullptr; h->eps_cap = 0;
-        if (cudaMalloc(&h->d_emax, (size_t)h->P * sizeof(unsigned)) != cudaSuccess ||
+        if (cudaMalloc(&h->d_emax, 2 * (size_t)h->P * kMaxT * sizeof(unsigned)) != cudaSuccess ||   // two banks x pairs x stages
             cudaMalloc(&h->d_stop, (size_t)h->P * sizeof(int)) != cudaSuccess) {
             cudaGetLastError();
             return fail(HSFLOW_ENOMEM, "cudaMalloc of the convergence words failed");
         }
         h->eps_cap = h->P;
     }
+    // layouts: single-sweep kernel emax[pair]; streaming kernel emax[bank][pair][kMaxT] with bank stride eps_cap * kMaxT
     CK(cudaMemsetAsync(h->d_emax + off, 0, (size_t)n * sizeof(unsigned), h->stream));
+    for (int bank = 0; bank < 2; ++bank)
+        CK(cudaMemsetAsync(h->d_emax + ((size_t)bank * h->eps_cap + off) * kMaxT, 0, (size_t)n * kMaxT * sizeof(unsigned), h->stream));
     CK(cudaMemsetAsync(h->d_stop + off, 0, (size_t)n * sizeof(int), h->stream));
+    h->ec_blk = 0;
     return HSFLOW_OK;
 }
 static int eps_guard(const hsflow* h) {
@@ -624,6 +633,25 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
             A.flag_dn = h->has_peer[1] ? (unsigned*)h->peer[1][2] + 0 : nullptr;   // we are its upper neighbour
             A.epoch = h->epoch;
         }
+        if (h->ec_on) {                            // EPS criterion: main launch + replay launch on the TRACK instantiation
+            if (h->connected || h->ov_u || t > kTrackT) return fail(HSFLOW_EINVAL, "internal: EPS block outside its envelope");
+            const StreamGeom GT = stream_geometry(kTrackT);
+            A.chunk_rows = chunk_rows_for(h, out_hi - out_lo, (h->W + GT.valid_w - 1) / GT.valid_w, n, kTrackT);
+            const int mt = GT.rows_per_box - 2;
+            const int bank = h->ec_blk & 1;
+            A.stop = h->d_stop; A.z_trk0 = h->ec_off;
+            A.emax = h->d_emax + (size_t)bank * h->eps_cap * kMaxT;
+            A.emax_next = h->d_emax + (size_t)(bank ^ 1) * h->eps_cap * kMaxT;
+            A.trk_t = t; A.trk_base = h->ec_sweep; A.trk_dst_parity = src == 0 ? 1 : 0; A.eps = h->eps;
+            const CUtensorMap& tuv = src == 0 ? h->tm_uvA[mt] : h->tm_uvB[mt];
+            A.trk_mode = 0;
+            CK(launch_jacobi_stream_track(h->stencil, tuv, h->tm_c[mt], A, n, h->stream));
+            A.trk_mode = 1;
+            CK(launch_jacobi_stream_track(h->stencil, tuv, h->tm_c[mt], A, n, h->stream));
+            h->launches += 2;
+            h->ec_blk++;
+            return HSFLOW_OK;
+        }
         const int m = G.rows_per_box - 2;
         if (m < 0 || m > 2) return fail(HSFLOW_EINVAL, "internal: no tensor map for %d-row boxes", G.rows_per_box);
         CK(launch_jacobi_stream(t, h->stencil, src == 0 ? h->tm_uvA[m] : h->tm_uvB[m], h->tm_c[m], A, n, h->stream));
@@ -740,7 +768,9 @@ int hsflow_iterate(hsflow_t* h, int n) {
         if (lo >= hi) return fail(HSFLOW_EINVAL, "ghost rows exhausted: refresh the halo (valid rows [%d,%d), block %d)", h->valid_lo, h->valid_hi, t);
         // the single-sweep path ping-pongs internally; keep the bookkeeping identical for both
         if (use_stream_kernel(h, t)) {
+            h->ec_on = h->eps > 0.0; h->ec_sweep = h->sweeps; h->ec_off = 0;
             int rc = run_block(h, t, h->cur, 0, h->P, lo, hi, h->zero_pending != 0);
+            h->ec_on = 0;
             if (rc) return rc;
             h->zero_pending = 0;
             h->cur ^= 1;
@@ -761,6 +791,8 @@ int hsflow_iterate(hsflow_t* h, int n) {
         h->valid_lo = lo; h->valid_hi = hi;
         n -= t;
     }
+    // EPS on the streaming kernel: pairs that stopped in the other ping-pong buffer move into the current one
+    if (eps_on_stream(h) && h->d_stop) { CK(launch_copy_stopped(h->uA, h->uB, h->uv_pp, h->d_stop, h->cur, h->P, h->stream)); h->launches += 2; }
     phase_end(h, HSFLOW_PHASE_ITER);
     return HSFLOW_OK;
 }
@@ -793,7 +825,9 @@ static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nu
         const int t = std::min(left, T);
         if (use_stream_kernel(h, t)) {
             if (left == t) { h->ov_u = fin_u; h->ov_v = fin_v; }
+            h->ec_on = h->eps > 0.0; h->ec_sweep = N - left; h->ec_off = p0;
             rc = run_block(h, t, src, p0, n, 0, h->H, zero_in);
+            h->ec_on = 0;
             zero_in = false;
             h->ov_u = h->ov_v = nullptr;
             if (rc) return rc;
@@ -810,6 +844,10 @@ static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nu
         left -= t;
     }
     if (src != 0) return fail(HSFLOW_ECUDA, "internal: sub-batch result not in the output planes");
+    if (eps_on_stream(h) && N > 0) {               // pairs that stopped in the B planes move into the A planes
+        CK(launch_copy_stopped(h->uA + (size_t)p0 * h->uv_pp, h->uB, h->uv_pp, h->d_stop + p0, 0, n, h->stream));
+        h->launches += 2;
+    }
     return HSFLOW_OK;
 }
 

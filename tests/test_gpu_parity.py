@@ -536,7 +536,7 @@ def test_epsilon_stop_fast_math_and_strip_mode_refusal(eng, P, oracle):
     we, wd, rho = _weights(P, P.STENCIL_CL8)
     uo, vo, it = oracle.jacobi_general_eps(*d, we, wd, rho, 400, 3e-3, True)
     eng.set_math(P.MATH_FAST).set_params(15.0, 400, P.STENCIL_CL8, True, 6).set_epsilon(3e-3)
-    assert eng.temporal_block == 1                      # EPS is checked after every sweep, as the reference does
+    assert eng.temporal_block == 4                      # FAST math: blocks of 4 tracked sweeps + replay
     eng.load_pair(f1, f2).compute()
     u, v = eng.read_uv()
     assert abs(eng.iterations_done() - it) <= 2 and it < 400
@@ -545,6 +545,71 @@ def test_epsilon_stop_fast_math_and_strip_mode_refusal(eng, P, oracle):
     with pytest.raises(P.HSFlowError):
         eng.prepare()
     eng.set_strip(True, True).set_epsilon(0.0)
+
+
+@pytest.mark.parametrize("stencil_name,W,H", [("cl8", 200, 96), ("cv4", 200, 96), ("cl8", 333, 70), ("cl8", 130, 9)])
+def test_epsilon_stop_on_blocked_kernel_equals_per_sweep_check_bitwise(P, oracle, stencil_name, W, H):
+    """cvTermCriteria(ITER | EPS) (OpticalFlowOpenCV.cpp:29) on the temporally blocked kernel: blocks of up to 4 sweeps
+    tracking every sweep's max-norm, and a replay of the block for the pair that met the criterion inside it, against
+    the single-sweep kernel that checks after every sweep (itself bit-identical to the oracle's sweep rule in EXACT
+    math): same sweep count, same field, for stops at every position inside a block, in either ping-pong buffer, for
+    the iteration cap, for tail blocks (max_iter % 4 != 0) and for a LITERAL-mode run."""
+    stencil = P.STENCIL_CL8 if stencil_name == "cl8" else P.STENCIL_CV4
+    f1, f2 = oracle.synth_pair(W, H, seed=23)
+    positions = set()
+    cases = [(e, m, True) for e in (8e-2, 5e-2, 3e-2, 2e-2, 1e-2, 6e-3, 4e-3, 2.5e-3) for m in (300,)]
+    cases += [(4e-3, 37, True), (1e-12, 41, True), (1e-12, 40, True), (0.5, 300, True), (1e9, 300, True), (6e-3, 300, False), (3e-2, 2, True)]
+    for eps, max_iter, upd in cases:
+        res = []
+        for kernel in (1, 0):                           # 1: single-sweep kernel only; 0: auto = blocked TRACK kernel
+            with P.HSFlow(0) as e:
+                e.set_kernel(kernel).set_params(15.0, max_iter, stencil, upd, 0).set_epsilon(eps)
+                if stencil == P.STENCIL_CV4:
+                    e.set_lambda(0.1)
+                assert e.temporal_block == (1 if kernel == 1 else 4)
+                l0 = e.kernel_launches
+                e.load_pair(f1, f2).compute()
+                res.append((e.iterations_done(), e.read_uv(), e.kernel_launches - l0))
+        (it1, (u1, v1), l1), (it4, (u4, v4), l4) = res
+        assert it1 == it4, (eps, max_iter, upd, it1, it4)
+        assert (bits(u1) == bits(u4)).all() and (bits(v1) == bits(v4)).all(), (eps, max_iter, upd, it1)
+        positions.add((it1 - 1) % 4 if it1 < max_iter else -1)
+    assert -1 in positions and len(positions - {-1}) >= 3, positions    # stops at (nearly) every position inside a block, and the cap
+
+
+def test_epsilon_stop_on_blocked_kernel_per_pair_batches_split_iterate_and_pipeline(P, oracle):
+    W, H, n, max_iter, eps = 144, 80, 6, 260, 6e-3
+    frames = np.empty((n, 2, H, W), np.uint8)
+    for k in range(n):
+        frames[k, 0], frames[k, 1] = oracle.synth_pair(W, H, seed=40 + 7 * k)
+    frames[3, 1] = frames[3, 0]                          # no motion: converges after the first sweep
+    want = []
+    with P.HSFlow(0) as e:
+        e.set_kernel(1).set_params(15.0, max_iter, P.STENCIL_CL8, True).set_epsilon(eps)
+        for k in range(n):
+            e.load_pair(frames[k, 0], frames[k, 1]).compute()
+            want.append((e.read_uv(), e.iterations_done()))
+    assert len({w[1] for w in want}) >= 3 and want[3][1] == 1
+    for sub in (0, 2):                                  # one sub-batch (prepare + iterate) / sub-batches of 2
+        with P.HSFlow(0) as e:
+            e.set_tuning(0, 0, sub).set_params(15.0, max_iter, P.STENCIL_CL8, True).set_epsilon(eps)
+            e.configure(W, H, n)
+            for k in range(n):
+                e.set_frames(frames[k, 0], frames[k, 1], pair=k)
+            if sub == 0:                                # the split form: iterate calls continue one session, odd split points
+                e.prepare(); e.iterate(101); e.iterate(2); e.iterate(max_iter - 103); e.sync()
+            else:
+                e.compute()
+            for k in range(n):
+                u, v = e.read_uv(k)
+                assert e.iterations_done(k) == want[k][1], (sub, k, e.iterations_done(k), want[k][1])
+                assert (bits(u) == bits(want[k][0][0])).all() and (bits(v) == bits(want[k][0][1])).all(), (sub, k)
+    with P.HSFlow(0) as e:                              # through the host pipeline (ragged sub-batches of 4)
+        e.set_tuning(0, 0, 4).set_params(15.0, max_iter, P.STENCIL_CL8, True).set_epsilon(eps)
+        u, v = np.empty((n, H, W), np.float32), np.empty((n, H, W), np.float32)
+        e.run_batch_host(frames, u, v)
+        for k in range(n):
+            assert (bits(u[k]) == bits(want[k][0][0])).all() and (bits(v[k]) == bits(want[k][0][1])).all(), k
 
 
 # ---- full-size frames: window check through the domain of dependence -----------------------------------------
