@@ -362,8 +362,10 @@ def run_ours(args, rank, world, local_rank):
     # ---- the box's own copy ceiling with all N ranks copying at once (plain pinned cudaMemcpyAsync) --------
     wire = pcie_ceiling(torch, dist, barrier)
     wire_bound = None
-    if wire and wire.get("d2h_gbs_concurrent"):
-        t_wire = 8.0 * W4K * H4K * ep / (wire["d2h_gbs_concurrent"] * 1e9)          # per rank, u and v of one step
+    if wire and wire.get("d2h_gbs"):
+        # upper bound of the full-field form: the 8 B per pixel of u, v cannot leave faster than a plain device -> host copy
+        # running ALONE on every rank (with the frame upload in flight the same link gives d2h_gbs_concurrent)
+        t_wire = 8.0 * W4K * H4K * ep / (wire["d2h_gbs"] * 1e9)                     # per rank, u and v of one step
         wire_bound = float(W4K) * H4K * ITER * ep * world / t_wire / 1e6
     del frames, uo, vo
 

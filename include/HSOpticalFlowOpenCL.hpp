@@ -43,8 +43,6 @@ class HSFLOW_CLASS HSOpticalFlowOpenCL {
     cl_float4* pixelData;        // staging plane of readInputImage (lane 0 = gray value)
     cl_float4* inputImageData1;
     cl_float4* inputImageData2;
-    cl_float4* u;                // flow as float4 planes, filled lazily for callers that read them
-    cl_float4* v;
     cl_float alpha;              // flow smoothness coefficient
     hsflow_t* engine;            // replaces cl_context / queue / 9 cl_mem / 3 cl_kernel (hpp:46-71)
     cl_uint width, height;

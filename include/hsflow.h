@@ -74,7 +74,8 @@ int hsflow_set_params(hsflow_t* h, float alpha, int iterations, int stencil, int
 int hsflow_set_lambda(hsflow_t* h, float lambda);         /* rho = 1/lambda (cv.cpp:29)          */
 int hsflow_set_math(hsflow_t* h, int math_mode);          /* HSFLOW_MATH_*                      */
 int hsflow_set_deriv(hsflow_t* h, int deriv_mode);        /* HSFLOW_DERIV_*                     */
-/* 0 = auto.  warps_per_cta is accepted and ignored: the streaming kernel always runs one autonomous warp per CTA. */
+/* 0 = auto.  warps_per_cta is accepted and ignored: the streaming kernel always runs one autonomous warp per CTA.
+ * sub_batch (pairs per launch / scratch size) takes effect at the next hsflow_configure. */
 int hsflow_set_tuning(hsflow_t* h, int chunk_rows, int warps_per_cta, int sub_batch);
 int hsflow_set_warm_start(hsflow_t* h, int keep_uv);      /* use_previous (cv.h:481-483)        */
 /* The EPS half of cvTermCriteria(CV_TERMCRIT_ITER | CV_TERMCRIT_EPS, it, 1e-6) (OpticalFlowOpenCV.cpp:29,
@@ -125,6 +126,10 @@ int hsflow_load_pair_f32(hsflow_t* h, const float* f1, const float* f2, int w, i
  * runCLKernels() x iterations, for every pair of the handle, without the per-iteration PCIe
  * round trip.  It is hsflow_prepare() followed by hsflow_iterate(iterations). */
 int hsflow_compute(hsflow_t* h);
+/* The same for pairs [p0, p0 + n) only (n <= hsflow_sub_batch()), asynchronously; the other pairs' frames and fields are
+ * not touched (fields of pairs no range has computed are unspecified).  Lets a caller overlap ingest of one half of
+ * the pair slots with compute on the other half. */
+int hsflow_compute_range(hsflow_t* h, int p0, int n);
 int hsflow_prepare(hsflow_t* h);            /* runDerivatives (cpp:321-474): coefficients; u = v = 0 */
 int hsflow_iterate(hsflow_t* h, int n);     /* n x runCLKernels (cpp:476-679)                         */
 /* Strip mode: after the caller refreshed the ghost rows of the current u/v planes. */

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libhsflow_host.so")
 EXE = os.path.join(HERE, "bin", "OpticalFlowHS")
 REF_MAIN = "/root/reference/OpticalFlowHS/main.cpp"
 CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-SRCS = ["HSOpticalFlowOpenCL.cpp", "OpticalFlowOpenCV.cpp", "hs_image.cpp"]
+SRCS = ["HSOpticalFlowOpenCL.cpp", "OpticalFlowOpenCV.cpp", "hs_image.cpp", "hs_ingest.cpp"]
 
 
 def _stale(target, deps):
@@ -30,7 +30,7 @@ def build(force=False):
     from . import build as core
     core.build()
     deps = [os.path.join(HOST, s) for s in SRCS + ["hs_image.h"]] + [
-        os.path.join(ROOT, "include", f) for f in ("hsflow.h", "HSOpticalFlowOpenCL.hpp", "OpticalFlowOpenCV.hpp")]
+        os.path.join(ROOT, "include", f) for f in ("hsflow.h", "hsflow_ingest.h", "HSOpticalFlowOpenCL.hpp", "OpticalFlowOpenCV.hpp")]
     if force or _stale(LIB, deps):
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
                f"-I{CUDA}/include", "-o", LIB] + [os.path.join(HOST, s) for s in SRCS] + [

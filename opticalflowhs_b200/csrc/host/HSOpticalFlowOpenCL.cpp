@@ -9,6 +9,7 @@
 
 #include <chrono>
 
+#include "../../../include/hsflow_ingest.h"
 #include "hs_image.h"
 
 namespace {
@@ -54,13 +55,13 @@ void hsflow_host_draw(std::vector<unsigned char>& img, int w, int h, const float
 
 HSOpticalFlowOpenCL::HSOpticalFlowOpenCL(const char* nm, char* src_, char* in1, char* in2, char* out,
                                          float alp, int it, int gs, char* dType)
-    : name(nm ? nm : ""), pixelData(NULL), inputImageData1(NULL), inputImageData2(NULL), u(NULL), v(NULL),
+    : name(nm ? nm : ""), pixelData(NULL), inputImageData1(NULL), inputImageData2(NULL),
       alpha(alp), engine(NULL), width(0), height(0), blockSizeX((size_t)gs), blockSizeY(1),
       src(src_), input1(in1), input2(in2), output(out), iterations(it),
       useGpu(!(dType && strcmp(dType, "CPU") == 0)), totalTime(0.0) {}
 
 HSOpticalFlowOpenCL::HSOpticalFlowOpenCL(const char* nm, char* src_, float alp, int it, int gs, char* dType)
-    : name(nm ? nm : ""), pixelData(NULL), inputImageData1(NULL), inputImageData2(NULL), u(NULL), v(NULL),
+    : name(nm ? nm : ""), pixelData(NULL), inputImageData1(NULL), inputImageData2(NULL),
       alpha(alp), engine(NULL), width(0), height(0), blockSizeX((size_t)gs), blockSizeY(1),
       src(src_), input1(NULL), input2(NULL), output(NULL), iterations(it),
       useGpu(!(dType && strcmp(dType, "CPU") == 0)), totalTime(0.0) {}
@@ -90,6 +91,9 @@ int HSOpticalFlowOpenCL::loadGray(const char* path, std::vector<unsigned char>& 
 
 // cpp:6-45: stage the current gray frame as float4 (lane 0 = value) into a fresh plane.
 int HSOpticalFlowOpenCL::readInputImage(cl_float4** inputImageData) {
+    // run() no longer keeps a host copy of the gray frame (it is decoded straight into HBM): callers of this legacy
+    // helper get it loaded here, from the second input (the frame run() stages last, cpp:732-740)
+    if (gray.empty() && input2) { int w = 0, h = 0; if (loadGray(input2, gray, w, h) == 0) { width = (cl_uint)w; height = (cl_uint)h; } }
     if (!inputImageData || gray.empty()) return SDK_FAILURE;
     const size_t n = (size_t)width * height;
     free(pixelData);
@@ -159,21 +163,24 @@ int HSOpticalFlowOpenCL::drawAndSave(const char* path) {
 int HSOpticalFlowOpenCL::run() {
     if (!src) return SDK_FAILURE;
     if (strcmp(src, "-hd") != 0) return runFrameSequence();
-    int w1 = 0, h1 = 0, w2 = 0, h2 = 0;
-    std::vector<unsigned char> g1, g2;
-    if (!input1 || loadGray(input1, g1, w1, h1) != 0) { std::cout << "Input image error.\n"; return -1; }   // cpp:722-725
-    if (!input2 || loadGray(input2, g2, w2, h2) != 0 || w2 != w1 || h2 != h1) { std::cout << "Input image error.\n"; return -1; }
-    width = (cl_uint)w1; height = (cl_uint)h1;
-    gray = g2;
+    if (!input1 || !input2) { std::cout << "Input image error.\n"; return -1; }
     std::cout << "przed setupCL\n";
     if (setupCL() != SDK_SUCCESS) return SDK_FAILURE;
     std::cout << "po setupCL\n";
+    // cvLoadImage + cvCvtColor + readInputImage (cpp:721-740): JPEGs are decoded on the GPU straight into the engine's
+    // BGR frame planes, PGM/PPM are uploaded as they are; the gray conversion runs inside the derivative kernel
+    int w1 = 0, h1 = 0;
+    if (hsingest_load_pair_files(engine, input1, input2, &w1, &h1) != HSFLOW_OK) {
+        std::cout << "Input image error.\n";                                             // cpp:722-725
+        return -1;
+    }
+    width = (cl_uint)w1; height = (cl_uint)h1;
+    gray.clear();
     const size_t n = (size_t)width * height;
     uHost.assign(n, 0.f); vHost.assign(n, 0.f);
-    // timed region of cpp:748-752: upload, derivatives, all iterations, read-back
+    // timed region of cpp:748-752: derivatives, all iterations, read-back
     const auto t0 = std::chrono::steady_clock::now();
-    int rc = hsflow_load_pair_gray8(engine, g1.data(), g2.data(), w1, h1, 0);
-    if (rc == HSFLOW_OK) rc = hsflow_compute(engine);
+    int rc = hsflow_compute(engine);
     if (rc == HSFLOW_OK) rc = hsflow_read_uv(engine, 0, uHost.data(), vHost.data(), 0);
     totalTime = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc != HSFLOW_OK) { std::cout << "hsflow: " << hsflow_last_error() << std::endl; return SDK_FAILURE; }
@@ -189,36 +196,33 @@ int HSOpticalFlowOpenCL::runFrameSequence() {
     const char* pattern = getenv("HSFLOW_FRAMES");
     if (!pattern) { fprintf(stderr, "ERROR: capture is NULL \n"); return -1; }   // cpp:779-783
     char path[1024];
-    std::vector<unsigned char> prev, cur;
     int w = 0, h = 0, count = 0;
     snprintf(path, sizeof path, pattern, 0);
-    if (loadGray(path, prev, w, h) != 0) { fprintf(stderr, "ERROR: frame is null...\n"); return -1; }
-    width = (cl_uint)w; height = (cl_uint)h;
     if (setupCL() != SDK_SUCCESS) return SDK_FAILURE;
+    // the first frame fills both planes (cpp:800-806 grabs one frame before the loop)
+    if (hsingest_load_pair_files(engine, path, path, &w, &h) != HSFLOW_OK) { fprintf(stderr, "ERROR: frame is null...\n"); return -1; }
+    width = (cl_uint)w; height = (cl_uint)h;
     uHost.assign((size_t)w * h, 0.f); vHost.assign((size_t)w * h, 0.f);
     double ms = 0;
-    if (hsflow_configure(engine, w, h, 1) != HSFLOW_OK || hsflow_push_frame_gray8(engine, prev.data(), 0) != HSFLOW_OK) {
-        std::cout << "hsflow: " << hsflow_last_error() << std::endl;
-        return SDK_FAILURE;
-    }
     for (int k = 1;; ++k) {
-        int w2 = 0, h2 = 0;
         snprintf(path, sizeof path, pattern, k);
-        if (loadGray(path, cur, w2, h2) != 0 || w2 != w || h2 != h) break;
+        FILE* probe = fopen(path, "rb");
+        if (!probe) break;
+        fclose(probe);
         const auto t0 = std::chrono::steady_clock::now();
         // cpp:834: the previous frame is already in HBM -- it becomes the first frame by a pointer swap, only the new
-        // frame crosses PCIe; u, v are re-zeroed per pair (cpp:331-332)
-        int rc = hsflow_push_frame_gray8(engine, cur.data(), 0);
-        if (rc == HSFLOW_OK) rc = hsflow_compute(engine);
+        // frame crosses PCIe (as a JPEG bitstream or as raw pixels); u, v are re-zeroed per pair (cpp:331-332)
+        int rc = hsingest_push_frame_file(engine, path);
+        if (rc != HSFLOW_OK) { std::cout << "hsflow: " << hsingest_last_error() << std::endl; break; }
+        rc = hsflow_compute(engine);
         if (rc == HSFLOW_OK) rc = hsflow_read_uv(engine, 0, uHost.data(), vHost.data(), 0);
         ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (rc != HSFLOW_OK) { std::cout << "hsflow: " << hsflow_last_error() << std::endl; return SDK_FAILURE; }
         const char* outp = getenv("HSFLOW_FRAMES_OUT");
         if (outp) { char op[1024]; snprintf(op, sizeof op, outp, k); drawAndSave(op); }
-        prev.swap(cur);                                                              // cpp:834
         ++count;
     }
-    gray = prev;
+    gray.clear();
     totalTime = count ? ms / count : 0.0;
     std::cout << "Avg time: " << totalTime << " [ms]" << std::endl;                  // cpp:838
     return SDK_SUCCESS;
@@ -227,7 +231,7 @@ int HSOpticalFlowOpenCL::runFrameSequence() {
 // cpp:849-892
 int HSOpticalFlowOpenCL::cleanup() {
     if (engine) { hsflow_destroy(engine); engine = NULL; }
-    free(pixelData); free(inputImageData1); free(inputImageData2); free(u); free(v);
-    pixelData = inputImageData1 = inputImageData2 = u = v = NULL;
+    free(pixelData); free(inputImageData1); free(inputImageData2);
+    pixelData = inputImageData1 = inputImageData2 = NULL;
     return SDK_SUCCESS;
 }

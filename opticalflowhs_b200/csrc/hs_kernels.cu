@@ -128,6 +128,16 @@ __global__ void __launch_bounds__(256) k_box3(const uint8_t* __restrict__ src, u
     dst[(size_t)blockIdx.z * pair_pitch + (size_t)y * row_pitch + x] = (uint8_t)__double2int_rn((double)sum * (1.0 / 9.0));
 }
 
+// cvCvtColor(CV_BGR2GRAY) of OpenCV 2.1 (cv.cpp:17, 20) for the OpenCV-mode path when the frames arrive as BGR
+__global__ void __launch_bounds__(256) k_bgr2gray(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int H,
+                                                   long long row_pitch, long long pair_pitch) {
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t r = (size_t)blockIdx.z * pair_pitch + (size_t)y * row_pitch;
+    const uint8_t* p = src + r + 3 * (size_t)x;
+    dst[r + x] = (uint8_t)((p[0] * 1868u + p[1] * 9617u + p[2] * 4899u + 8192u) >> 14);
+}
+
 __global__ void __launch_bounds__(256) k_deriv_cv(DerivArgs A) {
     const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y;
     if (x >= A.W || y >= A.H) return;
@@ -380,6 +390,11 @@ cudaError_t launch_deriv(const DerivArgs& A, int fmt, int pairs, cudaStream_t s)
 cudaError_t launch_box3(const uint8_t* src, uint8_t* dst, int W, int H, long long rp, long long pp, int pairs, cudaStream_t s) {
     dim3 blk(64, 4), grd((W + 63) / 64, (H + 3) / 4, pairs);
     k_box3<<<grd, blk, 0, s>>>(src, dst, W, H, rp, pp);
+    return cudaGetLastError();
+}
+cudaError_t launch_bgr2gray(const uint8_t* src, uint8_t* dst, int W, int H, long long rp, long long pp, int pairs, cudaStream_t s) {
+    dim3 blk(64, 4), grd((W + 63) / 64, (H + 3) / 4, pairs);
+    k_bgr2gray<<<grd, blk, 0, s>>>(src, dst, W, H, rp, pp);
     return cudaGetLastError();
 }
 cudaError_t launch_deriv_cv(const DerivArgs& A, int pairs, cudaStream_t s) {

@@ -101,6 +101,7 @@ struct StreamGeom {             // filled by stream_geometry()
 
 cudaError_t launch_deriv(const DerivArgs& A, int fmt, int pairs, cudaStream_t s);
 cudaError_t launch_box3(const uint8_t* src, uint8_t* dst, int W, int H, long long rp, long long pp, int pairs, cudaStream_t s);
+cudaError_t launch_bgr2gray(const uint8_t* src, uint8_t* dst, int W, int H, long long rp, long long pp, int pairs, cudaStream_t s);
 cudaError_t launch_deriv_cv(const DerivArgs& A, int pairs, cudaStream_t s);
 cudaError_t launch_jacobi1(const Jacobi1Args& A, bool exact, int stencil, bool update_v, int pairs, cudaStream_t s);
 // after sweep number `sweep` (1-based since prepare): stop[z] = (sweep << 1) | (sweep & 1) where emax[z] < eps; emax[z] = 0

@@ -80,7 +80,7 @@ struct hsflow {
     long long c_rp = 0, c_pp = 0;                  // coefficients: row pitch (3*pitch) and pair pitch, elements
     int top_edge = 1, bottom_edge = 1;
     // device memory
-    uint8_t *f1 = nullptr, *f2 = nullptr, *fb1 = nullptr, *fb2 = nullptr;
+    uint8_t *f1 = nullptr, *f2 = nullptr, *fb1 = nullptr, *fb2 = nullptr, *fg1 = nullptr, *fg2 = nullptr;   // frames, blurred, gray-of-BGR
     float *uA = nullptr, *vA = nullptr, *uB = nullptr, *vB = nullptr, *c0 = nullptr, *c1 = nullptr, *c2 = nullptr;
     float* dtmp = nullptr;                         // 3 planes of one pair, for hsflow_read_derivatives
     uint8_t* d_mask = nullptr;
@@ -144,7 +144,8 @@ static void strip_disconnect(hsflow* h) {
 
 static void free_planes(hsflow* h) {
     if (h->connected) strip_disconnect(h);         // the neighbours' mappings of OUR buffers die with the buffers: reconnect
-    cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2);
+    cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2); cudaFree(h->fg1); cudaFree(h->fg2);
+    h->fg1 = h->fg2 = nullptr;
     cudaFree(h->uA); cudaFree(h->uB); cudaFree(h->c0); cudaFree(h->dtmp);   // vA, vB, c1, c2 point into these
     cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0;
     h->f1 = h->f2 = h->fb1 = h->fb2 = nullptr;
@@ -330,8 +331,7 @@ int hsflow_set_tuning(hsflow_t* h, int chunk_rows, int warps_per_cta, int sub_ba
     NEED(h);
     if (chunk_rows < 0 || warps_per_cta < 0 || warps_per_cta > 8 || sub_batch < 0) return fail(HSFLOW_EINVAL, "bad tuning value");
     h->chunk_rows = chunk_rows; h->wpc = warps_per_cta;
-    if (sub_batch != h->sub_batch && h->P > 0) return fail(HSFLOW_EINVAL, "sub_batch must be set before hsflow_configure");
-    h->sub_batch = sub_batch;
+    h->sub_batch = sub_batch;                      // takes effect at the next hsflow_configure (which re-allocates when it changes S)
     return HSFLOW_OK;
 }
 int hsflow_set_kernel(hsflow_t* h, int which) {   /* 0 auto, 1 single-sweep kernel only, 2 streaming kernel even for T = 1 */
@@ -380,7 +380,7 @@ int hsflow_configure(hsflow_t* h, int W, int H, int P) {
     if (W <= 0 || H <= 0 || P <= 0) return fail(HSFLOW_EINVAL, "width, height, pairs must be positive");
     if (W > (1 << 24) || H > (1 << 24)) return fail(HSFLOW_EINVAL, "frame too large");
     CK(cudaSetDevice(h->device));
-    if (h->W == W && h->H == H && h->P == P && h->uA) {
+    if (h->W == W && h->H == H && h->P == P && h->uA && (h->sub_batch == 0 || h->S == std::min(h->sub_batch, P))) {
         h->prepared = 0;
         if (!h->connected) h->top_edge = h->bottom_edge = 1;   // a connected strip keeps its seams
         return HSFLOW_OK;
@@ -441,8 +441,8 @@ static int ensure_frames(hsflow* h, int fmt) {
     if (h->P <= 0) return fail(HSFLOW_EINVAL, "hsflow_configure first");
     if (h->fmt == fmt && h->f1) return HSFLOW_OK;
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2);
-    h->f1 = h->f2 = h->fb1 = h->fb2 = nullptr;
+    cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2); cudaFree(h->fg1); cudaFree(h->fg2);
+    h->f1 = h->f2 = h->fb1 = h->fb2 = h->fg1 = h->fg2 = nullptr;
     h->fmt = -1;                                   // no frame planes until both allocations succeeded
     h->prepared = 0;
     const int bpp = fmt == FMT_GRAY8 ? 1 : (fmt == FMT_BGR8 ? 3 : 4);
@@ -556,17 +556,33 @@ static int run_deriv(hsflow* h, int p0, int n, int normalise, float* o0, float* 
         CK(launch_deriv(A, h->fmt, n, h->stream));
         h->launches++;
     } else {
-        if (h->fmt != FMT_GRAY8) return fail(HSFLOW_EINVAL, "HSFLOW_DERIV_CV needs gray8 frames");
+        if (h->fmt != FMT_GRAY8 && h->fmt != FMT_BGR8) return fail(HSFLOW_EINVAL, "HSFLOW_DERIV_CV needs 8-bit frames (gray or BGR)");
         if (!h->top_edge || !h->bottom_edge) return fail(HSFLOW_EINVAL, "HSFLOW_DERIV_CV is not available in strip mode");
+        const size_t bytes = (size_t)h->f_pair_pitch * h->S;
         if (!h->fb1) {
-            const size_t bytes = (size_t)h->f_pair_pitch * h->S;
             if (cudaMalloc(&h->fb1, bytes) != cudaSuccess || cudaMalloc(&h->fb2, bytes) != cudaSuccess) {
                 cudaGetLastError();
+                cudaFree(h->fb1); cudaFree(h->fb2); h->fb1 = h->fb2 = nullptr;
                 return fail(HSFLOW_ENOMEM, "cudaMalloc of blur planes failed");
             }
         }
-        CK(launch_box3(f1base + (size_t)p0 * h->f_pair_pitch, h->fb1, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
-        CK(launch_box3(f2base + (size_t)p0 * h->f_pair_pitch, h->fb2, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
+        const uint8_t* g1 = f1base + (size_t)p0 * h->f_pair_pitch;
+        const uint8_t* g2 = f2base + (size_t)p0 * h->f_pair_pitch;
+        if (h->fmt == FMT_BGR8) {                  // cvCvtColor(CV_BGR2GRAY) (cv.cpp:17, 20) into gray planes of the same pitches
+            if (!h->fg1) {
+                if (cudaMalloc(&h->fg1, bytes) != cudaSuccess || cudaMalloc(&h->fg2, bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaFree(h->fg1); cudaFree(h->fg2); h->fg1 = h->fg2 = nullptr;
+                    return fail(HSFLOW_ENOMEM, "cudaMalloc of gray planes failed");
+                }
+            }
+            CK(launch_bgr2gray(g1, h->fg1, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
+            CK(launch_bgr2gray(g2, h->fg2, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
+            h->launches += 2;
+            g1 = h->fg1; g2 = h->fg2;
+        }
+        CK(launch_box3(g1, h->fb1, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
+        CK(launch_box3(g2, h->fb2, h->W, h->H, h->f_row_pitch, h->f_pair_pitch, n, h->stream));
         A.f1 = h->fb1; A.f2 = h->fb2;
         CK(launch_deriv_cv(A, n, h->stream));
         h->launches += 3;
@@ -872,6 +888,26 @@ int hsflow_compute(hsflow_t* h) {
     h->cur = 0;
     h->prepared = 0;
     h->zero_pending = 0; h->uv_valid = 1;
+    return HSFLOW_OK;
+}
+
+int hsflow_compute_range(hsflow_t* h, int p0, int n) {
+    NEED(h);
+    if (h->P <= 0 || !h->f1 || !h->f2) return fail(HSFLOW_EINVAL, "configure and load frames first");
+    if (p0 < 0 || n < 1 || p0 + n > h->P) return fail(HSFLOW_EINVAL, "pairs [%d, %d) outside the configured %d", p0, p0 + n, h->P);
+    if (n > h->S) return fail(HSFLOW_EINVAL, "a range holds at most sub_batch = %d pairs", h->S);
+    if (h->warm) return fail(HSFLOW_EINVAL, "warm start is not available for pair ranges");
+    if (!h->top_edge || !h->bottom_edge || h->connected) return fail(HSFLOW_EINVAL, "not available in strip mode");
+    CK(cudaSetDevice(h->device));
+    h->zero_pending = 0;
+    h->cur = 0;                                    // ranges always deliver into the result planes; a prepare/iterate session ends here
+    phase_begin(h, HSFLOW_PHASE_ITER);
+    int rc = compute_subbatch(h, p0, n);
+    if (rc) return rc;
+    phase_end(h, HSFLOW_PHASE_ITER);
+    h->sweeps = h->iterations;
+    h->prepared = 0;
+    h->uv_valid = 1;
     return HSFLOW_OK;
 }
 

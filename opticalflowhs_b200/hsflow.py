@@ -59,6 +59,7 @@ SIGNATURES = {
     "hsflow_load_pair_bgr8": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_size_t]),
     "hsflow_load_pair_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_size_t]),
     "hsflow_compute": (C.c_int, [_P]),
+    "hsflow_compute_range": (C.c_int, [_P, C.c_int, C.c_int]),
     "hsflow_prepare": (C.c_int, [_P]),
     "hsflow_iterate": (C.c_int, [_P, C.c_int]),
     "hsflow_halo_refreshed": (C.c_int, [_P]),
@@ -215,6 +216,9 @@ class HSFlow:
     # ---- compute
     def compute(self):
         self._ck(self._L.hsflow_compute(self._h)); return self
+
+    def compute_range(self, p0, n):
+        self._ck(self._L.hsflow_compute_range(self._h, p0, n)); return self
 
     def prepare(self):
         self._ck(self._L.hsflow_prepare(self._h)); return self

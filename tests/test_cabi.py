@@ -32,6 +32,26 @@ def test_header_symbols_are_exported_and_bound():
     assert L.hsflow_version() >= 100
 
 
+def test_ingest_header_symbols_are_exported_and_bound(tmp_path):
+    """include/hsflow_ingest.h (JPEG ingest on the GPU, libhsflow_host.so): every declared symbol is exported and bound,
+    and the header compiles as C99.  Loading needs libnvjpeg + libcudart, not a GPU."""
+    from opticalflowhs_b200 import build_host, ingest
+    build_host.build()
+    src = open(os.path.join(ROOT, "include", "hsflow_ingest.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(hsingest_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) >= 7
+    L = ingest.lib()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "opticalflowhs_b200", "libhsflow_host.so")], text=True)
+    exported = set(re.findall(r" T (hsingest_\w+)", out))
+    for n in names:
+        assert n in exported and hasattr(L, n), f"{n} declared in hsflow_ingest.h but not exported by libhsflow_host.so"
+        assert n in ingest.SIGNATURES, f"{n} missing from the ctypes binding"
+    c = tmp_path / "hi.c"
+    c.write_text('#include "%s"\nint main(void) { return hsingest_last_error() != 0 ? 0 : 1; }\n' % os.path.join(ROOT, "include", "hsflow_ingest.h"))
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-c", str(c), "-o", str(tmp_path / "hi.o")])
+
+
 def test_header_is_plain_c(tmp_path):
     """include/hsflow.h is the C ABI: it has to compile as C99 (cgo / JNI / ctypes-generator consumers), not only as C++."""
     src = tmp_path / "hc.c"

@@ -112,3 +112,113 @@ def test_image_io_pnm_exact_and_jpeg_roundtrip(tmp_path, oracle):
     back = read(tmp_path / "s.jpg")                       # nvJPEG encode -> nvJPEG decode
     assert back.shape == img.shape
     assert np.abs(back.astype(int) - img).mean() < 3.0
+
+
+# ---- f2 ingest: JPEG -> device frames without a host bounce (include/hsflow_ingest.h) -------------------------------
+
+def _jpeg_frames(oracle, n, W=320, H=200):
+    """Smooth colour frames (so that decoders agree to about one grey level) as JPEG bitstreams + the cv2 decode."""
+    cv2 = pytest.importorskip("cv2")
+    base, _ = oracle.synth_pair(W, H, seed=21)
+    base = cv2.GaussianBlur(base, (0, 0), 2.0)
+    streams, decoded = [], []
+    for k in range(n):
+        g = np.roll(base, (k, 2 * k), axis=(0, 1))
+        bgr = np.stack([g, np.roll(g, 3, 1), 255 - g], axis=2).copy()
+        ok, enc = cv2.imencode(".jpg", bgr, [cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+        assert ok
+        streams.append(enc.tobytes())
+        decoded.append(cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    return streams, decoded
+
+
+def test_jpeg_pair_decoded_on_gpu_into_frame_planes(tmp_path, oracle):
+    """hsingest_load_pair_jpeg / _files: nvJPEG writes BGR straight into the handle's planes, k_deriv<BGR8> does the gray
+    conversion.  Against (1) the oracle on the pixels the same decoder delivers to the host (tight) and (2) the oracle on
+    cv2.imdecode's pixels (another decoder: loose)."""
+    import opticalflowhs_b200 as P
+    from opticalflowhs_b200 import ingest
+    L = C.CDLL(HOSTLIB)
+    L.hsimg_read.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint8))]
+    streams, cvdec = _jpeg_frames(oracle, 2)
+    assert ingest.jpeg_info(streams[0]) == (320, 200, 3)
+    paths = []
+    for k, s in enumerate(streams):
+        paths.append(str(tmp_path / f"f{k}.jpg"))
+        with open(paths[-1], "wb") as f:
+            f.write(s)
+    host = []
+    for p in paths:                                       # the same decoder, delivered to the host by hsimg_read
+        w, h, ch, ptr = C.c_int(), C.c_int(), C.c_int(), C.POINTER(C.c_uint8)()
+        assert L.hsimg_read(p.encode(), C.byref(w), C.byref(h), C.byref(ch), C.byref(ptr)) == 0
+        host.append(np.ctypeslib.as_array(ptr, shape=(h.value, w.value, ch.value)).copy())
+        L.hsimg_free(ptr)
+    assert np.abs(host[0].astype(int) - cvdec[0]).mean() < 1.0        # nvJPEG vs libjpeg: about a grey level
+    N = 30
+    uo, vo = oracle.run_cl(oracle.bgr2gray(host[0]), oracle.bgr2gray(host[1]), 15.0, N, True)
+    uc, vc = oracle.run_cl(oracle.bgr2gray(cvdec[0]), oracle.bgr2gray(cvdec[1]), 15.0, N, True)
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 4)
+        for load in (lambda: ingest.load_pair_jpeg(e, streams[0], streams[1]), lambda: ingest.load_pair_files(e, paths[0], paths[1])):
+            load()
+            e.compute()
+            u, v = e.read_uv()
+            assert np.abs(u - uo).max() <= 1e-3 and np.abs(v - vo).max() <= 1e-3
+            assert np.abs(u - uc).mean() < 0.05 and np.abs(v - vc).mean() < 0.05
+        # OpenCV-mode path on BGR planes (k_bgr2gray + blur + Sobel estimator)
+        e.set_deriv(P.DERIV_CV).set_params(0.0, N, P.STENCIL_CV4, True, 4).set_lambda(0.1)
+        ingest.load_pair_jpeg(e, streams[0], streams[1])
+        e.compute()
+        u, v = e.read_uv()
+        uo, vo, _ = oracle.run_cv(oracle.bgr2gray(host[0]), oracle.bgr2gray(host[1]), 0.1, N, eps=0)
+        assert np.abs(u - uo).max() <= 1e-3 and np.abs(v - vo).max() <= 1e-3
+        # camera-loop step: swap + decode of the new frame only
+        e.set_deriv(P.DERIV_CL).set_params(15.0, N, P.STENCIL_CL8, True, 4)
+        ingest.load_pair_files(e, paths[0], paths[0])
+        ingest.push_frame_file(e, paths[1])
+        e.compute()
+        u, v = e.read_uv()
+        uo, vo = oracle.run_cl(oracle.bgr2gray(host[0]), oracle.bgr2gray(host[1]), 15.0, N, True)
+        assert np.abs(u - uo).max() <= 1e-3 and np.abs(v - vo).max() <= 1e-3
+
+
+def test_jpeg_video_batch_decode_overlapped_with_compute(oracle):
+    """hsingest_run_jpeg_batch: batched nvJPEG decode of the next chunk of pairs overlapping the compute of the current
+    one, pairs and consecutive-frame (sequence) layouts, full and sampled fields.  Checked against the oracle on cv2's
+    decode (other decoder: loose) and for consistency between the layouts (same decoder: exact)."""
+    import opticalflowhs_b200 as P
+    from opticalflowhs_b200 import ingest
+    n, N = 9, 20
+    streams, cvdec = _jpeg_frames(oracle, n, 256, 160)
+    gray = [oracle.bgr2gray(f) for f in cvdec]
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 4)
+        us, vs, st = ingest.run_jpeg_batch(e, streams, sequence=True)
+        assert us.shape == (n - 1, 160, 256) and st["images"] == n          # every frame decoded exactly once
+        for k in range(n - 1):
+            uo, vo = oracle.run_cl(gray[k], gray[k + 1], 15.0, N, True)
+            assert np.abs(us[k] - uo).mean() < 0.05 and np.abs(vs[k] - vo).mean() < 0.05, k
+        pairs = [s for k in range(n - 1) for s in (streams[k], streams[k + 1])]
+        up, vp, st = ingest.run_jpeg_batch(e, pairs, sequence=False)
+        assert st["images"] == 2 * (n - 1)
+        assert (up.view(np.uint32) == us.view(np.uint32)).all() and (vp.view(np.uint32) == vs.view(np.uint32)).all()
+        u4, v4, _ = ingest.run_jpeg_batch(e, streams, sequence=True, sample_step=4)
+        assert (u4.view(np.uint32) == us[:, ::4, ::4].view(np.uint32)).all() and (v4.view(np.uint32) == vs[:, ::4, ::4].view(np.uint32)).all()
+        with pytest.raises(P.HSFlowError):
+            ingest.run_jpeg_batch(e, streams[:1], sequence=True)
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="reference main.cpp binary not built")
+def test_unchanged_main_cv_camera_loop_reads_frame_files(tmp_path, oracle):
+    """OpticalFlowOpenCV::runFromCamera (cv.cpp:56-131) through the unchanged main: frames from HSFLOW_FRAMES, each paired
+    with the previous one, with and without use_previous."""
+    for k in range(4):
+        f1, _ = oracle.synth_pair(160, 120, seed=3, row0=0)
+        write_pgm(tmp_path / f"f{k:04d}.pgm", np.roll(f1, 2 * k, axis=1))
+    for warm in ("0", "1"):
+        r = run_main(["-cv", "-cam", "0.1", "20"], tmp_path,
+                     env={"HSFLOW_FRAMES": "f%04d.pgm", "HSFLOW_FRAMES_OUT": f"c{warm}_%04d.ppm", "HSFLOW_USE_PREVIOUS": warm})
+        assert r.returncode == 0 and "Avg time:" in r.stdout, r.stdout + r.stderr
+        assert all((tmp_path / f"c{warm}_{k:04d}.ppm").exists() for k in (1, 2, 3))
+    r = run_main(["-cv", "-cam", "0.1", "20"], tmp_path)              # no frame source: the reference's error path
+    assert "capture is NULL" in r.stdout + r.stderr
