@@ -90,6 +90,12 @@ int hsflow_set_epsilon(hsflow_t* h, double eps);
 /* 0 = auto; 1 = single-sweep kernel only (one launch per iteration); 2 = streaming kernel even for T = 1 */
 int hsflow_set_kernel(hsflow_t* h, int which);
 
+/* CUDA graphs: when hsflow_compute is asked for the same computation again (geometry, parameters, frame planes), the
+ * second call captures the launch sequence and every later one replays it with a single cudaGraphLaunch -- the win
+ * for launch-bound jobs (a 600 x 480 pair x 100 iterations is 26 launches).  0 = auto (jobs up to 4 Mi pixels),
+ * 1 = never, 2 = always. */
+int hsflow_set_graph(hsflow_t* h, int mode);
+
 /* ---- geometry: W x H frames, `pairs` independent frame pairs per handle ------------------ */
 int hsflow_configure(hsflow_t* h, int width, int height, int pairs);
 /* Row-strip of a taller frame: the handle's H rows are [own rows + ghost rows]; edges that are

@@ -59,6 +59,25 @@ struct StripBlob {
 static_assert(sizeof(StripBlob) <= sizeof(hsflow_strip_handle_t), "strip handle blob too large");
 constexpr uint32_t kStripMagic = 0x48534631u;   // "HSF1"
 
+// CUDA graphs for launch-bound jobs (small frames: 600x480 x 100 iterations is 1 + 25 launches of a few microseconds
+// each).  hsflow_compute replays a captured graph when the same computation -- same geometry, parameters and frame
+// planes -- comes again; everything that decides (the EPS criterion included) lives on the device, so the launch
+// sequence is the same every time.
+struct GraphKey {
+    int W, H, P, S, iterations, stencil, update_v, tblock, math, deriv, kernel_sel, chunk_rows, fmt, uv_dirty;
+    float rho;
+    double eps;
+    const void *f1, *f2;
+    bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof *this) == 0; }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    int final_cur = 0;
+    long long launches = 0;
+    unsigned long long stamp = 0;
+};
+
 struct hsflow {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, s_in = nullptr, s_out = nullptr;
@@ -126,6 +145,12 @@ struct hsflow {
     // without touching HBM (kZeroPair).  zero_pending = "the current buffer is logically zero but was not written":
     // everything else that looks at the buffer (read-back, single-sweep kernel, halo exchange by the caller)
     // materialises the zeros first.
+    int graph_mode = 0;                            // hsflow_set_graph: 0 auto (small jobs), 1 never, 2 always
+    int capturing = 0;                             // inside cudaStreamBeginCapture: no event timing
+    std::vector<GraphEntry> graphs;                // at most kMaxGraphs, least recently used goes first
+    GraphKey eager_key;                            // the computation that last ran eagerly (a repeat gets captured)
+    int have_eager_key = 0;
+    unsigned long long graph_stamp = 0;
     int zero_pending = 0;
     int uv_valid = 0;                              // the A/B planes hold a field a caller may read (not after pipelined calls)
     int coef_zero_b = 0;                           // the coefficient planes in memory were written with b = 0
@@ -142,7 +167,15 @@ static void strip_disconnect(hsflow* h) {
     cudaGetLastError();
 }
 
+constexpr size_t kMaxGraphs = 4;
+static void drop_graphs(hsflow* h) {               // device pointers baked into the graphs are about to die
+    for (GraphEntry& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+    h->have_eager_key = 0;
+}
+
 static void free_planes(hsflow* h) {
+    drop_graphs(h);
     if (h->connected) strip_disconnect(h);         // the neighbours' mappings of OUR buffers die with the buffers: reconnect
     cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2); cudaFree(h->fg1); cudaFree(h->fg2);
     h->fg1 = h->fg2 = nullptr;
@@ -214,8 +247,8 @@ static int materialize_zero(hsflow* h) {
     return HSFLOW_OK;
 }
 
-static void phase_begin(hsflow* h, int ph) { cudaEventRecord(h->ev0[ph], h->stream); }
-static void phase_end(hsflow* h, int ph) { cudaEventRecord(h->ev1[ph], h->stream); h->ev_set[ph] = 1; }
+static void phase_begin(hsflow* h, int ph) { if (!h->capturing) cudaEventRecord(h->ev0[ph], h->stream); }
+static void phase_end(hsflow* h, int ph) { if (!h->capturing) { cudaEventRecord(h->ev1[ph], h->stream); h->ev_set[ph] = 1; } }
 
 extern "C" {
 
@@ -340,6 +373,12 @@ int hsflow_set_kernel(hsflow_t* h, int which) {   /* 0 auto, 1 single-sweep kern
     h->kernel_sel = which;
     return HSFLOW_OK;
 }
+int hsflow_set_graph(hsflow_t* h, int mode) {
+    NEED(h);
+    if (mode < 0 || mode > 2) return fail(HSFLOW_EINVAL, "graph mode 0 (auto), 1 (never) or 2 (always)");
+    h->graph_mode = mode;
+    return HSFLOW_OK;
+}
 int hsflow_set_warm_start(hsflow_t* h, int keep) { NEED(h); h->warm = keep ? 1 : 0; return HSFLOW_OK; }
 int hsflow_set_epsilon(hsflow_t* h, double eps) {
     NEED(h);
@@ -441,6 +480,7 @@ static int ensure_frames(hsflow* h, int fmt) {
     if (h->P <= 0) return fail(HSFLOW_EINVAL, "hsflow_configure first");
     if (h->fmt == fmt && h->f1) return HSFLOW_OK;
     CK(cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
     cudaFree(h->f1); cudaFree(h->f2); cudaFree(h->fb1); cudaFree(h->fb2); cudaFree(h->fg1); cudaFree(h->fg2);
     h->f1 = h->f2 = h->fb1 = h->fb2 = h->fg1 = h->fg2 = nullptr;
     h->fmt = -1;                                   // no frame planes until both allocations succeeded
@@ -871,8 +911,83 @@ int hsflow_compute(hsflow_t* h) {
     NEED(h);
     if (h->P <= 0 || !h->f1 || !h->f2) return fail(HSFLOW_EINVAL, "configure and load frames first");
     if (h->P <= h->S) {
-        int rc = hsflow_prepare(h);
-        return rc ? rc : hsflow_iterate(h, h->iterations);
+        const bool small = (long long)h->W * h->H * h->P <= (4LL << 20);
+        const bool eligible = h->graph_mode != 1 && (h->graph_mode == 2 || small) && !h->warm && !h->connected && h->top_edge &&
+                              h->bottom_edge && h->iterations > 0;
+        if (!eligible) {
+            int rc = hsflow_prepare(h);
+            return rc ? rc : hsflow_iterate(h, h->iterations);
+        }
+        CK(cudaSetDevice(h->device));
+        GraphKey key;
+        memset(&key, 0, sizeof key);               // padding bytes take part in the comparison
+        key.W = h->W; key.H = h->H; key.P = h->P; key.S = h->S; key.iterations = h->iterations; key.stencil = h->stencil;
+        key.update_v = h->update_v; key.tblock = h->tblock; key.math = h->math; key.deriv = h->deriv; key.kernel_sel = h->kernel_sel;
+        key.chunk_rows = h->chunk_rows; key.fmt = h->fmt; key.uv_dirty = h->uv_dirty; key.rho = h->rho; key.eps = h->eps;
+        key.f1 = h->f1; key.f2 = h->f2;
+        GraphEntry* hit = nullptr;
+        for (GraphEntry& g : h->graphs) if (g.key == key) hit = &g;
+        if (!hit && !(h->have_eager_key && h->eager_key == key)) {
+            // first time: run eagerly (one-off allocations and attribute calls happen here, never inside a capture)
+            memcpy(&h->eager_key, &key, sizeof key); h->have_eager_key = 1;
+            h->cur = 0;                            // same starting buffer as the graph of this computation will use
+            int rc = hsflow_prepare(h);
+            return rc ? rc : hsflow_iterate(h, h->iterations);
+        }
+        if (!hit) {                                // second time: capture the launch sequence
+            h->cur = 0;
+            const long long l0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            h->capturing = 1;
+            int rc = hsflow_prepare(h);
+            if (!rc) rc = hsflow_iterate(h, h->iterations);
+            h->capturing = 0;
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            const long long captured = h->launches - l0;
+            h->launches = l0;                      // nothing ran yet: the replay below counts them
+            if (rc || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                h->graph_mode = 1;                 // do not try again on this handle
+                h->prepared = 0;
+                if (rc) return rc;
+                rc = hsflow_prepare(h);
+                return rc ? rc : hsflow_iterate(h, h->iterations);
+            }
+            GraphEntry g;
+            memcpy(&g.key, &key, sizeof key); g.final_cur = h->cur; g.launches = captured;
+            const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) {
+                cudaGetLastError();
+                h->graph_mode = 1;
+                h->cur = 0; h->prepared = 0;
+                rc = hsflow_prepare(h);
+                return rc ? rc : hsflow_iterate(h, h->iterations);
+            }
+            if (h->graphs.size() >= kMaxGraphs) {  // evict the least recently used
+                size_t lru = 0;
+                for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].stamp < h->graphs[lru].stamp) lru = i;
+                cudaGraphExecDestroy(h->graphs[lru].exec);
+                h->graphs.erase(h->graphs.begin() + (long)lru);
+            }
+            h->graphs.push_back(g);
+            hit = &h->graphs.back();
+        }
+        hit->stamp = ++h->graph_stamp;
+        phase_begin(h, HSFLOW_PHASE_ITER);
+        h->ev_set[HSFLOW_PHASE_DERIV] = 0;         // the graph runs as one piece: its time is reported as the iteration phase
+        CK(cudaGraphLaunch(hit->exec, h->stream));
+        phase_end(h, HSFLOW_PHASE_ITER);
+        h->launches += hit->launches;
+        h->cur = hit->final_cur;
+        h->valid_lo = 0; h->valid_hi = h->H;
+        h->sweeps = h->iterations;
+        h->zero_pending = 0; h->prepared = 1; h->uv_valid = 1;
+        h->coef_norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
+        h->coef_zero_b = (!h->update_v && use_stream_kernel(h, 1)) ? 1 : 0;
+        return HSFLOW_OK;
     }
     // batch larger than the scratch: sub-batches of S pairs; results always end in the A planes
     if (h->warm) return fail(HSFLOW_EINVAL, "warm start needs pairs <= sub_batch");

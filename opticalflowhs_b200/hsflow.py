@@ -45,6 +45,7 @@ SIGNATURES = {
     "hsflow_set_warm_start": (C.c_int, [_P, C.c_int]),
     "hsflow_set_epsilon": (C.c_int, [_P, C.c_double]),
     "hsflow_set_kernel": (C.c_int, [_P, C.c_int]),
+    "hsflow_set_graph": (C.c_int, [_P, C.c_int]),
     "hsflow_configure": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "hsflow_set_strip": (C.c_int, [_P, C.c_int, C.c_int]),
     "hsflow_set_frames_gray8": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
@@ -158,6 +159,10 @@ class HSFlow:
 
     def set_kernel(self, which):
         self._ck(self._L.hsflow_set_kernel(self._h, which)); return self
+
+    def set_graph(self, mode):
+        """CUDA graph replay of repeated computes: 0 auto (small jobs), 1 never, 2 always."""
+        self._ck(self._L.hsflow_set_graph(self._h, mode)); return self
 
     def set_warm_start(self, keep):
         self._ck(self._L.hsflow_set_warm_start(self._h, int(keep))); return self

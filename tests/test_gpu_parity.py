@@ -703,6 +703,50 @@ def test_16k_frame_500_iterations_windows_against_oracle_crops(P, oracle):
         assert du <= TOL_MAX and dv <= TOL_MAX, (y, x, du, dv)
 
 
+# ---- CUDA graph replay of repeated computes (launch-bound small frames) ------------------------------------------
+
+@pytest.mark.parametrize("mode", ["full", "literal", "eps", "exact"])
+def test_graph_replay_equals_eager_compute(P, oracle, mode):
+    """hsflow_compute on a small frame: first call eager, second captured into a CUDA graph, later ones replayed.  Every
+    call must give the eager result bit for bit -- also after the frame planes were rewritten in place, after the
+    camera-loop pointer swap (another graph), and with the EPS criterion deciding on the device inside the graph."""
+    W, H, N = 600, 480, 100
+    seq = [oracle.synth_pair(W, H, seed=60 + k)[0] for k in range(5)]
+
+    def make(graph_mode):
+        e = P.HSFlow(0)
+        e.set_graph(graph_mode).set_params(15.0, N, P.STENCIL_CL8, mode != "literal", 0)
+        if mode == "eps":
+            e.set_epsilon(2e-2)
+        if mode == "exact":
+            e.set_math(P.MATH_EXACT).set_params(15.0, 12, P.STENCIL_CL8, True, 0)
+        return e
+
+    ref, eng = make(1), make(0)
+    try:
+        for rep in range(4):                            # same planes, frames rewritten in place from the third call on
+            a, b = (seq[0], seq[1]) if rep < 2 else (seq[rep], seq[rep - 1])
+            for e in (ref, eng):
+                if rep == 0:
+                    e.load_pair(a, b)
+                elif rep >= 2:
+                    e.set_frames(a, b)
+                e.compute()
+            (u0, v0), (u1, v1) = ref.read_uv(), eng.read_uv()
+            assert (bits(u0) == bits(u1)).all() and (bits(v0) == bits(v1)).all(), rep
+            assert ref.iterations_done() == eng.iterations_done()
+        l0, l1 = ref.kernel_launches, eng.kernel_launches
+        ref.compute(); eng.compute()
+        assert ref.kernel_launches - l0 == eng.kernel_launches - l1      # a replay counts the launches it contains
+        for k in range(1, 5):                           # camera loop: the plane pointers swap with every frame
+            for e in (ref, eng):
+                e.push_frame(seq[k]).compute()
+            (u0, v0), (u1, v1) = ref.read_uv(), eng.read_uv()
+            assert (bits(u0) == bits(u1)).all() and (bits(v0) == bits(v1)).all(), k
+    finally:
+        ref.close(); eng.close()
+
+
 # ---- error behaviour of the boundary ------------------------------------------------------------------------------
 
 def test_error_codes_and_messages(eng, P):

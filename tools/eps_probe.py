@@ -27,7 +27,7 @@ for mode in ("cv", "cl"):
             for rep in range(6):
                 l0 = e.kernel_launches
                 e.compute(); e.sync()
-                ms.append(e.last_ms(1) + e.last_ms(2))
+                ms.append(max(e.last_ms(1), 0.0) + e.last_ms(2))
                 launches = e.kernel_launches - l0
             u, v = e.read_uv(0)
             rows[kernel] = (min(ms[2:]), e.iterations_done(0), launches, u, v)
