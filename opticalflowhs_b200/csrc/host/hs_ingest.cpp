@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 #include <nvjpeg.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <chrono>
@@ -38,23 +39,34 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // One decoder per process: a plain handle for single images and a batched state on the backend HSFLOW_NVJPEG_BACKEND
-// names ("default" | "hybrid" | "gpu" | "hardware"; default = "gpu": Huffman decoding on the GPU for baseline streams,
-// falling back to "default" when the library refuses it on this device).
+// names ("default" | "hybrid" | "gpu" | "hardware").  Default = "default" (nvJPEG's own choice: Huffman stage on the
+// host, IDCT + colour conversion on the GPU), with HSFLOW_NVJPEG_THREADS host threads (default: up to 16 of the cores
+// this process may use) working on the images of a batch in parallel.  Measured on the B200 boxes with 4K frames
+// (tools/ingest_probe.py, one host thread): default 58 images/s, GPU-assisted Huffman ("gpu") 25 images/s, the hardware
+// engine ("hardware") is refused by nvjpegCreateEx on this driver and falls back to default.
 struct Decoder {
     nvjpegHandle_t single = nullptr, batched = nullptr;
     nvjpegJpegState_t st_single = nullptr, st_batched = nullptr;
     cudaStream_t stream = nullptr;
-    int backend = 0, batch_size = 0;
+    int backend = 0, batch_size = 0, threads = 1;
     bool ok = false;
     Decoder() {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return;
         if (nvjpegCreateSimple(&single) != NVJPEG_STATUS_SUCCESS) return;
         if (nvjpegJpegStateCreate(single, &st_single) != NVJPEG_STATUS_SUCCESS) return;
         const char* want = getenv("HSFLOW_NVJPEG_BACKEND");
-        nvjpegBackend_t order[3] = {NVJPEG_BACKEND_GPU_HYBRID, NVJPEG_BACKEND_DEFAULT, NVJPEG_BACKEND_DEFAULT};
+        nvjpegBackend_t order[2] = {NVJPEG_BACKEND_DEFAULT, NVJPEG_BACKEND_DEFAULT};
         if (want && !strcmp(want, "hardware")) order[0] = NVJPEG_BACKEND_HARDWARE;
         else if (want && !strcmp(want, "hybrid")) order[0] = NVJPEG_BACKEND_HYBRID;
-        else if (want && !strcmp(want, "default")) order[0] = NVJPEG_BACKEND_DEFAULT;
+        else if (want && !strcmp(want, "gpu")) order[0] = NVJPEG_BACKEND_GPU_HYBRID;
+        const char* th = getenv("HSFLOW_NVJPEG_THREADS");
+        threads = th ? atoi(th) : 0;
+        if (threads <= 0) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            threads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : 1;
+            threads = std::max(1, std::min(threads, 16));
+        }
         for (nvjpegBackend_t b : order) {
             if (nvjpegCreateEx(b, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &batched) == NVJPEG_STATUS_SUCCESS &&
                 nvjpegJpegStateCreate(batched, &st_batched) == NVJPEG_STATUS_SUCCESS) {
@@ -121,7 +133,7 @@ int decode_batch(const uint8_t* const* jpegs, const size_t* sizes, uint8_t* cons
         if (iw != w || ih != h) return fail(HSFLOW_EINVAL, "image %d is %d x %d, expected %d x %d", k, iw, ih, w, h);
     }
     if (D.batch_size != n) {
-        const nvjpegStatus_t st = nvjpegDecodeBatchedInitialize(D.batched, D.st_batched, n, 1, NVJPEG_OUTPUT_BGRI);
+        const nvjpegStatus_t st = nvjpegDecodeBatchedInitialize(D.batched, D.st_batched, n, D.threads, NVJPEG_OUTPUT_BGRI);
         if (st != NVJPEG_STATUS_SUCCESS) return fail(HSFLOW_ECUDA, "nvjpegDecodeBatchedInitialize(%d) failed (%d)", n, (int)st);
         D.batch_size = n;
     }
@@ -331,7 +343,7 @@ int hsingest_run_jpeg_batch(hsflow_t* h, const uint8_t* const* jpegs, const size
     hsflow_set_stream(h, nullptr);
     cudaEventDestroy(ev);
     cudaStreamDestroy(cs);
-    if (stats) { stats[0] = decode_ms; stats[1] = (double)decoded; stats[2] = (double)B; stats[3] = (double)D.backend; }
+    if (stats) { stats[0] = decode_ms; stats[1] = (double)decoded; stats[2] = (double)B; stats[3] = (double)D.backend + 0.01 * D.threads; }
     return status;
 }
 

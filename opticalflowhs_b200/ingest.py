@@ -93,4 +93,4 @@ def run_jpeg_batch(engine, jpegs, sequence=False, sample_step=0):
                                        v.ctypes.data_as(_P), stats)
     engine.W, engine.H, engine.P = w, h, 0
     _ck(rc)
-    return u, v, {"decode_ms": stats[0], "images": int(stats[1]), "pairs_per_chunk": int(stats[2]), "backend": int(stats[3])}
+    return u, v, {"decode_ms": stats[0], "images": int(stats[1]), "pairs_per_chunk": int(stats[2]), "backend": int(stats[3]), "threads": int(round((stats[3] - int(stats[3])) * 100))}

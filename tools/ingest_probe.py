@@ -28,6 +28,6 @@ with P.HSFlow(0) as e:
     t0 = time.perf_counter()
     u, v, st = ingest.run_jpeg_batch(e, streams, sequence=True, sample_step=4)
     dt = time.perf_counter() - t0
-print(f"backend {os.environ.get('HSFLOW_NVJPEG_BACKEND', 'gpu (default choice)')} -> nvjpegBackend_t {st['backend']}: {N} frames {W}x{H} "
+print(f"backend {os.environ.get('HSFLOW_NVJPEG_BACKEND', 'default')} -> nvjpegBackend_t {st['backend']}, {st['threads']} host thread(s): {N} frames {W}x{H} "
       f"({mb:.1f} MB of JPEG), {IT} iterations: {dt * 1e3:.1f} ms total = {(N - 1) / dt:.1f} pairs/s, decode calls {st['decode_ms']:.1f} ms "
       f"({st['images'] / st['decode_ms'] * 1e3:.0f} images/s), {st['pairs_per_chunk']} pairs per chunk; finite: {bool(np.isfinite(u).all())}")
