@@ -179,6 +179,11 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     // chunk, pair, row range, TMA coordinates, ring phases) is warp-uniform BY CONSTRUCTION and the compiler keeps it
     // in uniform registers -- with warps sharing a CTA it cannot prove that, and the bookkeeping competes with the
     // pipeline state for vector registers (T = 6: 255 registers with spills -> 247 without, 10 % fewer instructions).
+    // Programmatic dependent launch: the next launch of the stream may start its CTAs as soon as SM resources free up,
+    // run everything that does not touch memory written by this one (index arithmetic, barrier initialisation) and
+    // then block in griddepcontrol.wait below until this grid has completed and flushed.  Hides the launch latency
+    // and the prologue of each of the ceil(N / T) launches of a computation, and fills the tail of the last wave.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x;
     const long long unit = blockIdx.x;
     if (unit >= A.total_units) return;
@@ -188,24 +193,6 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     const int z = (int)(tt / A.ncy);
     if (PEER && A.seam_first && A.ncy > 2) cy = cy == 0 ? 0 : (cy == 1 ? A.ncy - 1 : cy - 1);   // seam chunks run first
     const bool counted = !PEER || !A.seam_first || cy == 0 || cy == A.ncy - 1;
-    // EPS criterion (StreamArgs::stop ... eps): `lim` = stages that really iterate; the others pass their input through
-    int lim = T;
-    const int zt = TRACK ? A.z_trk0 + z : 0;
-    if constexpr (TRACK) {
-        const int st = A.stop[zt];
-        if (A.trk_mode == 0) {
-            if (st) return;                        // this pair met the criterion in an earlier block
-            lim = A.trk_t;
-        } else {
-            if (sx == 0 && cy == 0 && lane < kMaxT) A.emax_next[zt * kMaxT + lane] = 0u;
-            if (st && (st >> 1) <= A.trk_base) return;
-            int s = 0;                             // first sweep of the block whose max-norm fell below eps
-            while (s < A.trk_t && !((double)__uint_as_float(A.emax[zt * kMaxT + s]) < A.eps)) ++s;
-            if (s == A.trk_t) return;              // none: the main launch's result stands
-            lim = s + 1;
-            if (lane == 0) A.stop[zt] = ((A.trk_base + lim) << 1) | A.trk_dst_parity;   // every unit of the pair writes the same word
-        }
-    }
     const int W = A.W, H = A.H;
     const int R0 = A.out_lo + cy * A.chunk_rows;
     const int R1 = min(R0 + A.chunk_rows, A.out_hi);
@@ -252,6 +239,28 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
 #pragma unroll
         for (int i = 0; i < NGC + NGUV; ++i) mbar_init(bar0 + 8u * i, 1);
         fence_mbar_init();
+    }
+    // everything above is independent of the previous launch; from here on its results (u, v, stop words) are read
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // EPS criterion (StreamArgs::stop ... eps): `lim` = stages that really iterate; the others pass their input through
+    int lim = T;
+    const int zt = TRACK ? A.z_trk0 + z : 0;
+    if constexpr (TRACK) {
+        const int st = A.stop[zt];
+        if (A.trk_mode == 0) {
+            if (st) return;                        // this pair met the criterion in an earlier block
+            lim = A.trk_t;
+        } else {
+            if (sx == 0 && cy == 0 && lane < kMaxT) A.emax_next[zt * kMaxT + lane] = 0u;
+            if (st && (st >> 1) <= A.trk_base) return;
+            int s = 0;                             // first sweep of the block whose max-norm fell below eps
+            while (s < A.trk_t && !((double)__uint_as_float(A.emax[zt * kMaxT + s]) < A.eps)) ++s;
+            if (s == A.trk_t) return;              // none: the main launch's result stands
+            lim = s + 1;
+            if (lane == 0) A.stop[zt] = ((A.trk_base + lim) << 1) | A.trk_dst_parity;   // every unit of the pair writes the same word
+        }
+    }
+    if (lane == 0) {
         // A slot whose first box arrives in an odd virtual round gets one empty phase up front, so that
         // "parity = round & 1" holds for every slot.
 #pragma unroll

@@ -37,7 +37,14 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(HSFLOW_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
-#define NEED(h) do { if (!(h)) return fail(HSFLOW_EINVAL, "null handle"); } while (0)
+// Every entry point makes the handle's device current first: one process may drive handles on several GPUs
+// (LocalStripSolver: row strips of one frame over the GPUs of a box from a single host thread).
+#define NEED(h)                                                                                                   \
+    do {                                                                                                          \
+        if (!(h)) return fail(HSFLOW_EINVAL, "null handle");                                                      \
+        cudaError_t e_ = cudaSetDevice((h)->device);                                                              \
+        if (e_ != cudaSuccess) return fail(HSFLOW_ECUDA, "cudaSetDevice(%d): %s", (h)->device, cudaGetErrorString(e_)); \
+    } while (0)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1448,6 +1455,7 @@ int hsflow_push_frame_gray8(hsflow_t* h, const uint8_t* frame, size_t pitch) {
 
 float hsflow_last_ms(hsflow_t* h, int phase) {
     if (!h || phase < 0 || phase > 3 || !h->ev_set[phase]) return -1.f;
+    cudaSetDevice(h->device);
     if (cudaEventSynchronize(h->ev1[phase]) != cudaSuccess) return -1.f;
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, h->ev0[phase], h->ev1[phase]) != cudaSuccess) { cudaGetLastError(); return -1.f; }

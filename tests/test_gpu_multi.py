@@ -84,3 +84,34 @@ def test_row_strips_with_peer_stores_bit_identical_to_one_gpu(tmp_path, T, ghost
     u = np.concatenate([np.load(tmp_path / f"u{r}.npy") for r in range(world)])
     v = np.concatenate([np.load(tmp_path / f"v{r}.npy") for r in range(world)])
     assert (u.view(np.uint32) == whole[0].view(np.uint32)).all() and (v.view(np.uint32) == whole[1].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("T,N,rows", [(6, 60, 400), (4, 22, 130), (0, 45, 1030)])
+def test_row_strips_driven_by_one_process_over_several_gpus(T, N, rows):
+    """LocalStripSolver: ONE process, one handle per GPU, strips connected through the same-process branch of
+    hsflow_strip_connect (cudaDeviceEnablePeerAccess instead of CUDA IPC).  The iteration kernel on GPU k stores its
+    seam rows into the buffers of GPUs k - 1 and k + 1 over NVLink.  Bit-identical to the whole frame on one GPU."""
+    world = min(_ngpu(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import opticalflowhs_b200 as P
+    from opticalflowhs_b200.sharding import LocalStripSolver
+    W, H = 3000, rows * world + 9
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, T)
+        e.configure(W, H, 1).synth_frames(0, 0, 4321).compute()
+        whole = e.read_uv()
+    engs = [P.HSFlow(d) for d in range(world)]
+    try:
+        for e in engs:
+            e.set_params(15.0, N, P.STENCIL_CL8, True, T)
+        s = LocalStripSolver(engs, W, H, 6 if T == 0 else T)
+        s.load_synth(4321)
+        for rep in range(2):
+            s.run(N).sync()
+            u, v = s.gather_uv()
+            assert (u.view(np.uint32) == whole[0].view(np.uint32)).all() and (v.view(np.uint32) == whole[1].view(np.uint32)).all(), rep
+        s.close()
+    finally:
+        for e in engs:
+            e.close()

@@ -8,6 +8,7 @@ longest work unit, not bytes.
 import os
 import statistics
 import sys
+import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opticalflowhs_b200 as P  # noqa: E402
@@ -29,4 +30,20 @@ for W, H in sizes:
             print(f"kernel={kern} T={T} chunk={chunk:3d}: {1e3 * m:8.1f} us  ({W * H * N / m / 1e3:9.0f} Mpx-it/s)", flush=True)
         except Exception as ex:
             print(f"kernel={kern} T={T} chunk={chunk}: {ex}")
+    # whole computes (derivative pass + all iterations), host wall clock over 50 back-to-back calls: eager launches
+    # against CUDA-graph replay (hsflow_set_graph); HSFLOW_NO_PDL=1 in the environment switches programmatic dependent
+    # launch off for the same comparison
+    e.set_kernel(0).set_tuning(0, 0, 0).set_params(15.0, N, 0, True, 0)
+    for graph, name in ((1, "eager launches"), (2, "graph replay")):
+        e.set_graph(graph)
+        for _ in range(3):
+            e.compute()
+        e.sync()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            e.compute()
+        e.sync()
+        us = (time.perf_counter() - t0) / 50 * 1e6
+        print(f"compute() {name:15s} PDL {'off' if os.environ.get('HSFLOW_NO_PDL') else 'on '}: {us:8.1f} us per pair  ({W * H * N / us:9.0f} Mpx-it/s)", flush=True)
+    e.set_graph(0)
 e.close()
