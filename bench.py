@@ -195,6 +195,25 @@ def run_reference(args, rank):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
+def gpu_cpu_affinity(local_rank):
+    """CPU list `nvidia-smi topo -m` reports as this GPU's affinity (the cores of the socket it hangs off), or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            cols = line.split()
+            if cols and cols[0] == f"GPU{local_rank}":
+                for c in cols[1:]:
+                    if c[0].isdigit() and ("-" in c or "," in c):
+                        cpus = set()
+                        for part in c.split(","):
+                            a, _, b = part.partition("-")
+                            cpus.update(range(int(a), int(b or a) + 1))
+                        return cpus
+    except Exception:
+        pass
+    return None
+
+
 def bind_to_gpu_numa_node(torch, local_rank):
     """Pin this rank's threads (and with them its pinned host buffers, which are placed on the allocating thread's
     node) to the CPU socket its GPU hangs off: with 8 ranks the host-buffer traffic of the e2e leg otherwise crosses
@@ -217,6 +236,17 @@ def bind_to_gpu_numa_node(torch, local_rank):
             return node
     except Exception:
         pass
+    # no NUMA information in sysfs (containers): fall back to the driver's view of the topology
+    try:
+        cpus = gpu_cpu_affinity(local_rank)
+        allowed = (cpus or set()) & os.sched_getaffinity(0)
+        if allowed and allowed != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, allowed)
+            return f"cpus {min(allowed)}-{max(allowed)} (nvidia-smi topo)"
+        if cpus is not None and not allowed:
+            return "gpu's socket is outside this container's cpuset"
+    except Exception:
+        pass
     return None
 
 
@@ -229,6 +259,7 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)               # the CPU legs at the end get every core back
     numa_node = bind_to_gpu_numa_node(torch, local_rank)
     print(f"[bench] rank {rank}: GPU {local_rank} on host NUMA node {numa_node}, {len(os.sched_getaffinity(0))} CPUs", file=sys.stderr)
     dist = None
@@ -368,6 +399,11 @@ def run_ours(args, rank, world, local_rank):
         t_wire = 8.0 * W4K * H4K * ep / (wire["d2h_gbs"] * 1e9)                     # per rank, u and v of one step
         wire_bound = float(W4K) * H4K * ITER * ep * world / t_wire / 1e6
     del frames, uo, vo
+
+    try:                                             # before any OpenMP thread of the CPU legs is born
+        os.sched_setaffinity(0, all_cpus)
+    except Exception:
+        pass
 
     # ---- BASELINE.json configs[4] rides along: the strip-sharded 16K frame at this N ----------------------
     strip = None

@@ -40,8 +40,8 @@ int fail(int code, const char* fmt, ...) {
 
 // One decoder per process: a plain handle for single images and a batched state on the backend HSFLOW_NVJPEG_BACKEND
 // names ("default" | "hybrid" | "gpu" | "hardware").  Default = "default" (nvJPEG's own choice: Huffman stage on the
-// host, IDCT + colour conversion on the GPU), with HSFLOW_NVJPEG_THREADS host threads (default: up to 16 of the cores
-// this process may use) working on the images of a batch in parallel.  Measured on the B200 boxes with 4K frames
+// host, IDCT + colour conversion on the GPU), with HSFLOW_NVJPEG_THREADS host threads (default 1: 16 threads decoded the
+// same 56-58 images/s).  Measured on the B200 boxes with 4K frames
 // (tools/ingest_probe.py, one host thread): default 58 images/s, GPU-assisted Huffman ("gpu") 25 images/s, the hardware
 // engine ("hardware") is refused by nvjpegCreateEx on this driver and falls back to default.
 struct Decoder {
@@ -64,8 +64,8 @@ struct Decoder {
         if (threads <= 0) {
             cpu_set_t set;
             CPU_ZERO(&set);
-            threads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : 1;
-            threads = std::max(1, std::min(threads, 16));
+            threads = 1;                           // measured: more threads do not speed nvjpegDecodeBatched up on this backend
+            (void)set;
         }
         for (nvjpegBackend_t b : order) {
             if (nvjpegCreateEx(b, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &batched) == NVJPEG_STATUS_SUCCESS &&
