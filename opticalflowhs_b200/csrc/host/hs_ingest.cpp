@@ -11,11 +11,13 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "hs_image.h"
@@ -39,16 +41,16 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // One decoder per process: a plain handle for single images and a batched state on the backend HSFLOW_NVJPEG_BACKEND
-// names ("default" | "hybrid" | "gpu" | "hardware").  Default = "default" (nvJPEG's own choice: Huffman stage on the
-// host, IDCT + colour conversion on the GPU), with HSFLOW_NVJPEG_THREADS host threads (default 1: 16 threads decoded the
-// same 56-58 images/s).  Measured on the B200 boxes with 4K frames
-// (tools/ingest_probe.py, one host thread): default 58 images/s, GPU-assisted Huffman ("gpu") 25 images/s, the hardware
-// engine ("hardware") is refused by nvjpegCreateEx on this driver and falls back to default.
+// names ("default" | "hybrid" | "gpu" | "hardware"; default = "default": Huffman stage on the host, IDCT + colour
+// conversion on the GPU).  Batches first try the parallel decoupled path below (decode_parallel) and fall back to
+// nvjpegDecodeBatched.  Measured on the B200 boxes with 4K frames (tools/ingest_probe.py), nvjpegDecodeBatched: default
+// 56-58 images/s with 1 or 16 library threads, GPU-assisted Huffman ("gpu") 25 images/s; the hardware engine
+// ("hardware") is refused by nvjpegCreateEx on this driver and falls back to default.
 struct Decoder {
     nvjpegHandle_t single = nullptr, batched = nullptr;
     nvjpegJpegState_t st_single = nullptr, st_batched = nullptr;
     cudaStream_t stream = nullptr;
-    int backend = 0, batch_size = 0, threads = 1;
+    int backend = 0, batch_size = 0, threads = 1, last_path = 0;   // last_path 1: parallel decoupled decode, 0: nvjpegDecodeBatched
     bool ok = false;
     Decoder() {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return;
@@ -122,6 +124,95 @@ int decode_one(const uint8_t* jpeg, size_t len, uint8_t* d_bgr, size_t pitch, in
     return HSFLOW_OK;
 }
 
+// ---- parallel decode: nvJPEG's decoupled API, one worker context per host thread -------------------------------------
+// The Huffman stage of the hybrid decoder runs on the host and is what bounds a 4K clip (17 ms per frame on one core,
+// against 1 ms of Horn-Schunck compute per pair): HSFLOW_NVJPEG_THREADS workers (default: the cores this process may
+// use, at most 16) each own a decoder state with its pinned and device buffers and a CUDA stream, take images off a
+// shared counter, run the host stage (nvjpegDecodeJpegHost) and queue the device stages (transfer, IDCT, colour
+// conversion straight into the destination plane) on their stream.
+struct Worker {
+    nvjpegJpegDecoder_t dec = nullptr;
+    nvjpegJpegState_t st = nullptr;
+    nvjpegBufferPinned_t pin = nullptr;
+    nvjpegBufferDevice_t dev = nullptr;
+    nvjpegJpegStream_t js = nullptr;
+    nvjpegDecodeParams_t par = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool ok = false;
+    bool init(nvjpegHandle_t h) {
+        if (nvjpegDecoderCreate(h, NVJPEG_BACKEND_HYBRID, &dec) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegDecoderStateCreate(h, dec, &st) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegBufferPinnedCreate(h, nullptr, &pin) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegBufferDeviceCreate(h, nullptr, &dev) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegJpegStreamCreate(h, &js) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegDecodeParamsCreate(h, &par) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegDecodeParamsSetOutputFormat(par, NVJPEG_OUTPUT_BGRI) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegStateAttachPinnedBuffer(st, pin) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegStateAttachDeviceBuffer(st, dev) != NVJPEG_STATUS_SUCCESS) return false;
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) return false;
+        return ok = true;
+    }
+};
+struct Pool {
+    std::vector<Worker> w;
+    int device = 0;
+    bool tried = false;
+};
+Pool& pool() { static Pool p; return p; }
+
+int pool_threads() {
+    const char* th = getenv("HSFLOW_NVJPEG_THREADS");
+    int n = th ? atoi(th) : 0;
+    if (n <= 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        n = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : 1;
+        n = std::min(n, 16);
+    }
+    return std::max(1, n);
+}
+
+// returns HSFLOW_OK, or a negative code when the parallel path cannot take this batch (the caller falls back)
+int decode_parallel(const uint8_t* const* jpegs, const size_t* sizes, uint8_t* const* dsts, int n, size_t pitch) {
+    Decoder& D = dec();
+    Pool& P = pool();
+    const int want = std::min(pool_threads(), n);
+    if (want < 2) return HSFLOW_EINVAL;
+    if (!P.tried) {
+        P.tried = true;
+        cudaGetDevice(&P.device);
+        P.w.resize((size_t)pool_threads());
+        for (Worker& wk : P.w) if (!wk.init(D.single)) { P.w.clear(); break; }
+    }
+    if (P.w.empty()) return HSFLOW_EINVAL;
+    std::atomic<int> next(0), failed(0);
+    auto body = [&](Worker* wk) {
+        cudaSetDevice(P.device);
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n || failed.load()) break;
+            nvjpegImage_t img;
+            memset(&img, 0, sizeof img);
+            img.channel[0] = dsts[i]; img.pitch[0] = pitch;
+            bool ok = nvjpegJpegStreamParse(D.single, jpegs[i], sizes[i], 0, 0, wk->js) == NVJPEG_STATUS_SUCCESS &&
+                      nvjpegDecodeJpegHost(D.single, wk->dec, wk->st, wk->par, wk->js) == NVJPEG_STATUS_SUCCESS &&
+                      nvjpegDecodeJpegTransferToDevice(D.single, wk->dec, wk->st, wk->js, wk->stream) == NVJPEG_STATUS_SUCCESS &&
+                      nvjpegDecodeJpegDevice(D.single, wk->dec, wk->st, &img, wk->stream) == NVJPEG_STATUS_SUCCESS;
+            // the state's pinned buffer is reused by the next image of this worker: its transfer has to be over
+            if (ok) ok = cudaStreamSynchronize(wk->stream) == cudaSuccess;
+            if (!ok) { failed.store(1); break; }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < want; ++k) th.emplace_back(body, &P.w[(size_t)k]);
+    body(&P.w[0]);
+    for (std::thread& t : th) t.join();
+    if (failed.load()) { cudaGetLastError(); return HSFLOW_ECUDA; }
+    return HSFLOW_OK;                              // every worker stream is idle: the planes are complete
+}
+
 // Batched decode of `n` bitstreams into `n` device destinations (all w x h, pitch bytes per row), on D.stream.
 int decode_batch(const uint8_t* const* jpegs, const size_t* sizes, uint8_t* const* dsts, int n, size_t pitch, int w, int h) {
     Decoder& D = dec();
@@ -132,6 +223,8 @@ int decode_batch(const uint8_t* const* jpegs, const size_t* sizes, uint8_t* cons
         if (rc) return rc;
         if (iw != w || ih != h) return fail(HSFLOW_EINVAL, "image %d is %d x %d, expected %d x %d", k, iw, ih, w, h);
     }
+    if (decode_parallel(jpegs, sizes, dsts, n, pitch) == HSFLOW_OK) { D.last_path = 1; return HSFLOW_OK; }
+    D.last_path = 0;
     if (D.batch_size != n) {
         const nvjpegStatus_t st = nvjpegDecodeBatchedInitialize(D.batched, D.st_batched, n, D.threads, NVJPEG_OUTPUT_BGRI);
         if (st != NVJPEG_STATUS_SUCCESS) return fail(HSFLOW_ECUDA, "nvjpegDecodeBatchedInitialize(%d) failed (%d)", n, (int)st);
@@ -343,7 +436,7 @@ int hsingest_run_jpeg_batch(hsflow_t* h, const uint8_t* const* jpegs, const size
     hsflow_set_stream(h, nullptr);
     cudaEventDestroy(ev);
     cudaStreamDestroy(cs);
-    if (stats) { stats[0] = decode_ms; stats[1] = (double)decoded; stats[2] = (double)B; stats[3] = (double)D.backend + 0.01 * D.threads; }
+    if (stats) { stats[0] = decode_ms; stats[1] = (double)decoded; stats[2] = (double)B; stats[3] = (double)D.backend + 0.01 * (D.last_path ? std::min(pool_threads(), 99) : 1); }
     return status;
 }
 
