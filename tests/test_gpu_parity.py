@@ -356,6 +356,45 @@ def test_pipelined_bgr_frames_and_sampled_fields(P, oracle, sequence):
                 assert (bits(vs[k]) == bits(want[k][1][::step, ::step])).all(), (step, k)
 
 
+def test_compute_range_on_pair_slots_and_frames_written_on_the_device(P, oracle):
+    """hsflow_compute_range (two halves of the pair slots computed independently -- what the JPEG ingest uses to overlap
+    decode and compute) and the device-side frame entries hsflow_map_frames / hsflow_set_frames_*_dev, against per-pair
+    computes; torch only moves bytes into the mapped planes."""
+    import torch
+    from opticalflowhs_b200.sharding import DeviceView
+    W, H, n, N = 200, 64, 6, 13
+    pairs = [oracle.synth_pair(W, H, seed=90 + k) for k in range(n)]
+    want = []
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 4)
+        for f1, f2 in pairs:
+            e.load_pair(f1, f2).compute()
+            want.append(e.read_uv())
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 4).set_tuning(sub_batch=3).configure(W, H, n)
+        assert e.sub_batch == 3
+        d1, d2, rp, pp = e.map_frames(bgr=False)
+        for k, (f1, f2) in enumerate(pairs):             # write the frames into the mapped planes on the device
+            for base, f in ((d1, f1), (d2, f2)):
+                plane = torch.as_tensor(DeviceView(base + k * pp, (H, rp), "|u1"), device="cuda")
+                plane[:, :W].copy_(torch.from_numpy(f).cuda())
+        torch.cuda.synchronize()
+        e.compute_range(3, 3).compute_range(0, 3).sync()
+        for k in range(n):
+            u, v = e.read_uv(k)
+            assert (bits(u) == bits(want[k][0])).all() and (bits(v) == bits(want[k][1])).all(), k
+        with pytest.raises(P.HSFlowError):
+            e.compute_range(0, 4)                        # more than sub_batch pairs
+        with pytest.raises(P.HSFlowError):
+            e.compute_range(4, 3)                        # outside the configured pairs
+        # device-to-device entry with BGR frames
+        bgr = np.stack([pairs[0][0]] * 3, axis=2).copy(), np.stack([pairs[0][1]] * 3, axis=2).copy()
+        t1, t2 = torch.from_numpy(bgr[0]).cuda(), torch.from_numpy(bgr[1]).cuda()
+        e.configure(W, H, 1).set_frames_bgr_dev(t1.data_ptr(), t2.data_ptr(), 3 * W).compute()
+        u, v = e.read_uv()
+        assert (bits(u) == bits(want[0][0])).all() and (bits(v) == bits(want[0][1])).all()
+
+
 # ---- strips: host-mediated halo exchange on one GPU ---------------------------------------------------
 
 def test_frame_sequence_pipeline_and_push_frame_equal_per_pair_compute(P, oracle):
