@@ -62,6 +62,19 @@ cudaError_t launch_jacobi_stream_track(int stencil, const CUtensorMap& tuv, cons
     return stream_launch_track(stencil, tuv, tc, A, s);
 }
 
+bool stream_seam_first(int T, const StreamArgs& A) {
+    const int rows = A.out_hi - A.out_lo;
+    if (A.done_counter == nullptr || rows <= 0 || A.chunk_rows <= 0) return false;
+    const int ncy = (rows + A.chunk_rows - 1) / A.chunk_rows;
+    if (ncy < 2 || A.chunk_rows < T) return false;
+    // Rows [0, up_lo) and [dn_hi, H) are ghost rows the neighbours store into; [up_lo, up_hi) and [dn_lo, dn_hi)
+    // are the rows this strip pushes.  Early signalling is safe when only the first and the last chunk touch them.
+    const int first_end = A.out_lo + A.chunk_rows, last_start = A.out_lo + (ncy - 1) * A.chunk_rows;
+    const bool top_ok = A.peer_up == nullptr || first_end >= std::max(A.up_hi, A.up_lo + T);
+    const bool bot_ok = A.peer_dn == nullptr || last_start <= std::min(A.dn_lo, A.dn_hi - T);
+    return top_ok && bot_ok;
+}
+
 cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tuv, const CUtensorMap& tc, StreamArgs A, int pairs,
                                  cudaStream_t s) {
     const StreamGeom G = stream_geometry(T);
@@ -72,16 +85,11 @@ cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tuv, con
     A.total_units = (long long)A.nsx * A.ncy * pairs;
     A.seam_first = 0;
     A.signal_units = A.total_units;
-    if (A.done_counter != nullptr && A.ncy >= 2 && A.chunk_rows >= T) {
-        // Rows [0, up_lo) and [dn_hi, H) are ghost rows the neighbours store into; [up_lo, up_hi) and [dn_lo, dn_hi)
-        // are the rows this strip pushes.  Early signalling is safe when only the first and the last chunk touch them.
-        const int first_end = A.out_lo + A.chunk_rows, last_start = A.out_lo + (A.ncy - 1) * A.chunk_rows;
-        const bool top_ok = A.peer_up == nullptr || first_end >= std::max(A.up_hi, A.up_lo + T);
-        const bool bot_ok = A.peer_dn == nullptr || last_start <= std::min(A.dn_lo, A.dn_hi - T);
-        if (top_ok && bot_ok) {
-            A.seam_first = 1;
-            A.signal_units = (long long)A.nsx * 2 * pairs;
-        }
+    if (stream_seam_first(T, A)) {
+        A.seam_first = 1;
+        A.signal_units = (long long)A.nsx * 2 * pairs;
+    } else {
+        A.wait_up = A.wait_dn = nullptr;               // the in-kernel seam wait needs the seam-first order
     }
     const bool peer = A.done_counter != nullptr;    // strip connected to its neighbours (hsflow_strip_connect)
     switch (T) {

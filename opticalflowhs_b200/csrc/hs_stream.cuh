@@ -260,6 +260,32 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             if (lane == 0) A.stop[zt] = ((A.trk_base + lim) << 1) | A.trk_dst_parity;   // every unit of the pair writes the same word
         }
     }
+    if constexpr (PEER) {
+        // In-kernel seam wait (StreamArgs::wait_up / wait_dn): only the units of the top and bottom row chunks read
+        // ghost rows and push seam rows; they wait until the neighbour on their side published the previous epoch.
+        // The neighbour runs on another GPU and never waits for THIS launch, so the wait cannot cycle.
+        const unsigned* w = !A.seam_first ? nullptr : (cy == 0 ? A.wait_up : (cy == A.ncy - 1 ? A.wait_dn : nullptr));
+        if (w != nullptr) {
+            if (lane == 0) {
+                const unsigned need = A.epoch - 1u;
+                auto seen = [&]() {
+                    unsigned x;
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(w) : "memory");
+                    return x;
+                };
+                if ((int)(seen() - need) < 0) {
+                    const uint64_t t0 = globaltimer_ns();
+                    while ((int)(seen() - need) < 0) {
+                        __nanosleep(200);
+                        if (globaltimer_ns() - t0 > 3 * kMbarTimeoutNs) __trap();   // a neighbour that never comes: fail loudly
+                    }
+                }
+                // the neighbour's rows were written through the generic proxy; this unit reads them with TMA
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            __syncwarp();
+        }
+    }
     if (lane == 0) {
         // A slot whose first box arrives in an odd virtual round gets one empty phase up front, so that
         // "parity = round & 1" holds for every slot.

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -132,6 +133,8 @@ struct hsflow {
     int push_lo[2] = {}, push_hi[2] = {}, push_delta[2] = {};
     int connected = 0;
     unsigned epoch = 0;
+    unsigned waited_epoch = 0;                     // neighbours' epoch the stream has already waited for (cuStreamWaitValue32)
+    int seam_inkernel = 0;                         // all neighbours live on other devices: seam units wait in the kernel instead
     // EPS termination (hsflow_set_epsilon): per-pair device words, see Jacobi1Args
     double eps = 0.0;
     unsigned* d_emax = nullptr;
@@ -666,6 +669,24 @@ static int chunk_rows_for(const hsflow* h, int rows, int nsx, int pairs, int T) 
     return best_ch;
 }
 
+// Peer transport: make the handle's stream wait until both neighbours published epoch `e` (their seam rows of that
+// launch are in our buffer, and they finished reading the rows our later launches push into).  No host involvement,
+// no spinning kernel.
+static int strip_stream_wait(hsflow* h, unsigned e) {
+    if ((int)(h->waited_epoch - e) >= 0) return HSFLOW_OK;
+    for (int d = 0; d < 2; ++d)
+        if (h->has_peer[d]) {
+            // FLUSH: the neighbour's seam rows were written over NVLink BEFORE the flag; the next kernel on this stream
+            // must see them, which the driver only guarantees with the flush flag (where supported -- otherwise the
+            // ordering rests on the writer's __threadfence_system + st.release.sys alone).
+            CUresult r = h->wait_value((CUstream)h->stream, (CUdeviceptr)(h->sig + d), e,
+                                       CU_STREAM_WAIT_VALUE_GEQ | (h->can_flush ? CU_STREAM_WAIT_VALUE_FLUSH : 0));
+            if (r != CUDA_SUCCESS) return fail(HSFLOW_ECUDA, "cuStreamWaitValue32 failed with CUresult %d", (int)r);
+        }
+    h->waited_epoch = e;
+    return HSFLOW_OK;
+}
+
 // one launch advancing t iterations for n pairs.  src/dst: 0 = A planes (pair offset pA), 1 = B planes (offset 0)
 static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int out_hi, bool zero_in = false) {
     float* uo = src == 0 ? h->uB : h->uA + (size_t)pA * h->uv_pp;
@@ -695,6 +716,16 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
             A.flag_up = h->has_peer[0] ? (unsigned*)h->peer[0][2] + 1 : nullptr;   // we are its lower neighbour
             A.flag_dn = h->has_peer[1] ? (unsigned*)h->peer[1][2] + 0 : nullptr;   // we are its upper neighbour
             A.epoch = h->epoch;
+            // This launch needs the neighbours' previous epoch.  Neighbours on other GPUs + seam chunks first: the seam
+            // units wait for it inside the kernel and the launch overlaps the tail of its predecessor (programmatic
+            // dependent launch).  Otherwise the stream waits.
+            if (h->seam_inkernel && stream_seam_first(t, A)) {
+                A.wait_up = h->has_peer[0] ? h->sig + 0 : nullptr;
+                A.wait_dn = h->has_peer[1] ? h->sig + 1 : nullptr;
+            } else {
+                int rc = strip_stream_wait(h, h->epoch - 1u);
+                if (rc) return rc;
+            }
         }
         if (h->ec_on) {                            // EPS criterion: main launch + replay launch on the TRACK instantiation
             if (h->connected || h->ov_u || t > kTrackT) return fail(HSFLOW_EINVAL, "internal: EPS block outside its envelope");
@@ -807,17 +838,11 @@ int hsflow_iterate(hsflow_t* h, int n) {
             h->zero_pending = 0;
             h->cur ^= 1;
             h->sweeps += t;
-            for (int d = 0; d < 2; ++d)
-                if (h->has_peer[d]) {
-                    // FLUSH: the neighbour's seam rows were written over NVLink BEFORE the flag; the next kernel on this
-                    // stream must see them, which the driver only guarantees with the flush flag (where supported --
-                    // otherwise the ordering rests on the writer's __threadfence_system + st.release.sys alone).
-                    CUresult r = h->wait_value((CUstream)h->stream, (CUdeviceptr)(h->sig + d), h->epoch,
-                                               CU_STREAM_WAIT_VALUE_GEQ | (h->can_flush ? CU_STREAM_WAIT_VALUE_FLUSH : 0));
-                    if (r != CUDA_SUCCESS) return fail(HSFLOW_ECUDA, "cuStreamWaitValue32 failed with CUresult %d", (int)r);
-                }
             n -= t;
         }
+        // end of the call: the stream catches up with both neighbours, so that whatever follows on it (read-back, a
+        // new hsflow_prepare) sees a quiescent seam
+        { int rc = strip_stream_wait(h, h->epoch); if (rc) return rc; }
         h->valid_lo = 0; h->valid_hi = h->H;
         phase_end(h, HSFLOW_PHASE_ITER);
         return HSFLOW_OK;
@@ -1044,6 +1069,7 @@ int hsflow_strip_export(hsflow_t* h, hsflow_strip_handle_t* out) {
     CK(cudaMemsetAsync(h->sig, 0, 256, h->stream));
     CK(cudaStreamSynchronize(h->stream));          // the words are zero before any neighbour can see them
     h->epoch = 0;
+    h->waited_epoch = 0;
     StripBlob b;
     memset(&b, 0, sizeof b);
     b.magic = kStripMagic; b.W = h->W; b.H = h->H; b.device = h->device; b.pitch = h->pitch; b.pid = (int64_t)getpid();
@@ -1103,6 +1129,20 @@ int hsflow_strip_connect(hsflow_t* h, const hsflow_strip_handle_t* up, int up_lo
     }
     h->top_edge = h->has_peer[0] ? 0 : 1;
     h->bottom_edge = h->has_peer[1] ? 0 : 1;
+    {
+        // In-kernel seam wait only when every neighbour runs on another GPU (kernels of one GPU must never wait for each
+        // other: nothing guarantees they run at the same time); HSFLOW_STRIP_WAIT=stream forces stream waits (profilers
+        // that serialise kernels need that), =kernel forces the in-kernel wait.
+        int other = 1;
+        for (int d = 0; d < 2; ++d) {
+            if (!blobs[d]) continue;
+            StripBlob b;
+            memcpy(&b, blobs[d], sizeof b);
+            if (b.device == h->device) other = 0;
+        }
+        const char* env = getenv("HSFLOW_STRIP_WAIT");
+        h->seam_inkernel = env && !strcmp(env, "stream") ? 0 : (env && !strcmp(env, "kernel") ? 1 : other);
+    }
     h->connected = 1;
     h->prepared = 0;
     return HSFLOW_OK;
