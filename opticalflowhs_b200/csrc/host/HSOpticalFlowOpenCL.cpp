@@ -7,6 +7,7 @@
 // (the reference moves u and v over PCIe twice per iteration, cpp:483-501, 655-675).
 #include "../../../include/HSOpticalFlowOpenCL.hpp"
 
+#include <algorithm>
 #include <chrono>
 
 #include "../../../include/hsflow_ingest.h"
@@ -21,19 +22,76 @@ inline void put(std::vector<unsigned char>& img, int w, int h, int x, int y, con
     unsigned char* p = &img[((size_t)y * w + x) * 3];
     p[0] = c[0]; p[1] = c[1]; p[2] = c[2];
 }
+// cvCircle(img, centre, 2, colour, -1): the filled circle of radius 2 as OpenCV rasterises it -- 13 pixels, rows of
+// 1, 3, 5, 3, 1 (|dx| + |dy| <= 2), not the 21-pixel Euclidean disc.
 void filledCircle2(std::vector<unsigned char>& img, int w, int h, int cx, int cy, const unsigned char* c) {
-    for (int dy = -2; dy <= 2; ++dy)              // cvCircle(.., 2, .., -1): the 21-pixel disc
+    for (int dy = -2; dy <= 2; ++dy)
         for (int dx = -2; dx <= 2; ++dx)
-            if (dx * dx + dy * dy <= 5) put(img, w, h, cx + dx, cy + dy, c);
+            if (std::abs(dx) + std::abs(dy) <= 2) put(img, w, h, cx + dx, cy + dy, c);
 }
-void line8(std::vector<unsigned char>& img, int w, int h, int x0, int y0, int x1, int y1, const unsigned char* c) {
-    int dx = std::abs(x1 - x0), sx = x0 < x1 ? 1 : -1, dy = -std::abs(y1 - y0), sy = y0 < y1 ? 1 : -1, err = dx + dy;
-    for (int guard = 0; guard < 1 << 20; ++guard) {   // Bresenham, 8-connected
-        put(img, w, h, x0, y0, c);
-        if (x0 == x1 && y0 == y1) break;
-        const int e2 = 2 * err;
-        if (e2 >= dy) { err += dy; x0 += sx; }
-        if (e2 <= dx) { err += dx; y0 += sy; }
+
+// cv::clipLine: Cohen-Sutherland against [0, w-1] x [0, h-1], intersection points computed in double and truncated
+bool clipLine(int w, int h, long long& x1, long long& y1, long long& x2, long long& y2) {
+    const long long right = w - 1, bottom = h - 1;
+    if (w <= 0 || h <= 0) return false;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (long long)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (long long)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (long long)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (long long)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// cvLine(img, p1, p2, colour, 1, 8): OpenCV's LineIterator -- the line is clipped to the image first, always walked
+// from its left end point to its right one, one pixel per step along the major axis, the minor axis steps when the
+// integer error term (starting at dx - 2 dy) is negative.
+void line8(std::vector<unsigned char>& img, int w, int h, int ax, int ay, int bx, int by, const unsigned char* c) {
+    long long x1 = ax, y1 = ay, x2 = bx, y2 = by;
+    if ((unsigned long long)x1 >= (unsigned long long)w || (unsigned long long)x2 >= (unsigned long long)w ||
+        (unsigned long long)y1 >= (unsigned long long)h || (unsigned long long)y2 >= (unsigned long long)h) {
+        if (!clipLine(w, h, x1, y1, x2, y2)) return;
+    }
+    long long dx = x2 - x1, dy = y2 - y1;
+    if (dx < 0) { dx = -dx; dy = -dy; x1 = x2; y1 = y2; }     // left to right
+    int sx = 1, sy = 1;
+    if (dy < 0) { dy = -dy; sy = -1; }
+    const bool steep = dy > dx;                                 // the major axis is y
+    const long long major = steep ? dy : dx, minor = steep ? dx : dy;
+    long long err = major - (minor + minor);
+    const long long plusDelta = major + major, minusDelta = -(minor + minor);
+    long long x = x1, y = y1;
+    for (long long k = 0; k <= major; ++k) {
+        put(img, w, h, (int)x, (int)y, c);
+        const bool neg = err < 0;
+        err += minusDelta + (neg ? plusDelta : 0);
+        if (steep) { y += sy; if (neg) x += sx; }
+        else { x += sx; if (neg) y += sy; }
     }
 }
 }  // namespace
@@ -48,9 +106,23 @@ void hsflow_host_draw(std::vector<unsigned char>& img, int w, int h, const float
             const float a = u[(size_t)i * w + j], b = v[(size_t)i * w + j];
             if (a > thr || b > thr || a < -thr || b < -thr) {
                 filledCircle2(img, w, h, j, i, kCircleBGR);
-                line8(img, w, h, j, i, (int)(j + a * lineScale), (int)(i + b * lineScale), kLineBGR);
+                // cvPoint(x + u, y + v): int + float evaluated by the reference's x87 build in extended precision, then
+                // truncated; double keeps that (float would round a fraction just below 1 up to the next integer)
+                const double ex = std::min(std::max((double)j + (double)a * (double)lineScale, -1e9), 1e9);
+                const double ey = std::min(std::max((double)i + (double)b * (double)lineScale, -1e9), 1e9);
+                line8(img, w, h, j, i, (int)ex, (int)ey, kLineBGR);
             }
         }
+}
+
+// C entry for tests and other bindings: bgr_out receives w * h * 3 bytes
+extern "C" __attribute__((visibility("default"))) int hsimg_draw_flow(const float* u, const float* v, int w, int h, float thr,
+                                                                      float line_scale, unsigned char* bgr_out) {
+    if (!u || !v || !bgr_out || w <= 0 || h <= 0) return -1;
+    std::vector<unsigned char> img;
+    hsflow_host_draw(img, w, h, u, v, thr, line_scale);
+    memcpy(bgr_out, img.data(), img.size());
+    return 0;
 }
 
 HSOpticalFlowOpenCL::HSOpticalFlowOpenCL(const char* nm, char* src_, char* in1, char* in2, char* out,

@@ -8,12 +8,17 @@
  * Parity status: PINNED.
  *   - hso_derivatives / hso_jacobi (Kernels.cl semantics) are checked bit-for-bit against
  *     the reference's own Kernels.cl compiled for the host (oracle/clref_shim.cpp ->
- *     oracle/_ref/libclref.so) and against the shipped *_cl_out.jpg dot masks
- *     (tests/golden/, IoU 1.000).
+ *     oracle/_ref/libclref.so) and against the shipped *_cl_out.jpg pictures: drawn like
+ *     HSOpticalFlowOpenCL.cpp:758-770 and saved like cvSaveImage, the fields reproduce EVERY PIXEL of
+ *     OpticalFlowHS/{city,bunny}_cl_out.jpg and Release/bunny_cl_out.jpg (tests/golden/pictures.npz).
  *   - hso_cvhs (OpenCV 2.1 cvCalcOpticalFlowHS, third-party cv210.dll, source NOT under
- *     /root/reference) is a restatement of the published/disassembled algorithm and is only
- *     weakly pinned by the shipped *_cv_out.jpg masks (IoU >= 0.98).  "parity unpinned by
- *     tests" for that function; it is the looser cross-check and a reported CPU baseline.
+ *     /root/reference) is a restatement of the disassembled algorithm.  It is pinned by the
+ *     reference's own outputs as well: with both 3x3 blurs, lambda = 0.1, 10 iterations its fields, drawn like
+ *     OpticalFlowOpenCV.cpp:32-46 and saved like cvSaveImage, reproduce EVERY PIXEL of
+ *     OpticalFlowHS/{city,bunny}_cv_out.jpg (threshold decisions of all grid points, end points
+ *     trunc(x + u/2) of the 950 / 1955 drawn lines); N +- 1 or no blur change thousands of pixels
+ *     (tests/test_oracle.py).  Not pinned: the EPS termination rule (the shipped pictures ran into the
+ *     iteration cap) and use_previous.
  */
 #ifndef HS_ORACLE_H_
 #define HS_ORACLE_H_

@@ -251,3 +251,31 @@ def window_error(u_win, v_win, W, H, N, seed, y, x, alpha=15.0, update_v=True, f
     K = u_win.shape[0]
     uo, vo = window_reference(W, H, N, seed, y, x, K, alpha, update_v, frames)
     return float(np.abs(u_win - uo).max()), float(np.abs(v_win - vo).max())
+
+
+# ---- the drawing loop of the reference, for picture-level known-answer tests ---------------------------------------
+
+def render_flow(u, v, thr, line_scale, step=4):
+    """The output picture of the reference: HSOpticalFlowOpenCL.cpp:758-770 (thr 0.5, line to (j + u, i + v)) and
+    OpticalFlowOpenCV.cpp:32-46 (thr 1, line to (x + u/2, y + v/2)): black image; on the stride-4 grid, where
+    |u| > thr or |v| > thr, a filled blue circle of radius 2 and a red 8-connected line whose end point is truncated to
+    int like cvPoint(float, float) does.  Drawn with cv2.circle / cv2.line (same rasterisers as the OpenCV 2.1 C API)."""
+    import cv2
+    h, w = u.shape
+    img = np.zeros((h, w, 3), np.uint8)
+    for y in range(0, h, step):
+        for x in range(0, w, step):
+            a, b = float(u[y, x]), float(v[y, x])
+            if a > thr or b > thr or a < -thr or b < -thr:
+                cv2.circle(img, (x, y), 2, (255, 0, 0), -1)                       # CV_RGB(0,0,255), cpp:3
+                # int + float, evaluated in extended precision by the reference's x87 build, truncated by cvPoint
+                cv2.line(img, (x, y), (int(x + a * float(line_scale)), int(y + b * float(line_scale))), (0, 0, 255), 1, 8)   # CV_RGB(255,0,0), cpp:4
+    return img
+
+
+def jpeg_roundtrip(img_bgr, quality=95):
+    """cvSaveImage(path.jpg) with its default quality, then cvLoadImage: what a shipped *_out.jpg holds."""
+    import cv2
+    ok, enc = cv2.imencode(".jpg", img_bgr, [cv2.IMWRITE_JPEG_QUALITY, quality])
+    assert ok
+    return cv2.imdecode(enc, cv2.IMREAD_COLOR)

@@ -25,6 +25,11 @@ def masks():
 
 
 @pytest.fixture(scope="session")
+def pictures():
+    return dict(np.load(os.path.join(GOLDEN, "pictures.npz")))
+
+
+@pytest.fixture(scope="session")
 def fields():
     return dict(np.load(os.path.join(GOLDEN, "fields.npz")))
 

@@ -9,6 +9,10 @@
                 (OpticalFlowHS/{city,bunny}_cl_out.jpg, Release/bunny_cl_out.jpg, *_cv_out.jpg):
                 a dot is present at (i, j) iff >= 5 of the 3x3 pixels centred there have
                 max(B,G,R) > 120 (the blue filled circle of cpp:766 / cv.cpp:42).
+  pictures.npz: the five shipped OUTPUT pictures decoded (cv2.imread), BGR uint8.  They are exact known-answer vectors
+                for BOTH paths: drawing the oracle's fields like cpp:758-770 / cv.cpp:32-46 (cv2.circle + cv2.line),
+                JPEG-encoding at quality 95 (the cvSaveImage default) and decoding again reproduces every pixel of
+                *_cl_out.jpg (alpha = 15, N = 10 / 2, LITERAL) and of *_cv_out.jpg (lambda = 0.1, N = 10, eps 1e-6).
   fields.npz  : u/v produced HERE by the reference's own Kernels.cl compiled for the host
                 (oracle/_ref/libclref.so): city pair, alpha=15, N=100, LITERAL and FULL modes,
                 sampled on the stride-4 drawing grid; and bunny N=10.
@@ -58,6 +62,15 @@ def main():
     }
     np.savez_compressed(os.path.join(HERE, "masks.npz"), **masks)
 
+    pictures = {
+        "city_cl_a15_n10": cv2.imread(f"{REF}/OpticalFlowHS/city_cl_out.jpg", 1),
+        "bunny_cl_a15_n10": cv2.imread(f"{REF}/OpticalFlowHS/bunny_cl_out.jpg", 1),
+        "bunny_cl_a15_n2": cv2.imread(f"{REF}/Release/bunny_cl_out.jpg", 1),
+        "city_cv_l0.1_n10": cv2.imread(f"{REF}/OpticalFlowHS/city_cv_out.jpg", 1),
+        "bunny_cv_l0.1_n10": cv2.imread(f"{REF}/OpticalFlowHS/bunny_cv_out.jpg", 1),
+    }
+    np.savez_compressed(os.path.join(HERE, "pictures.npz"), **pictures)
+
     fields = {}
     for name, n in (("city", 100), ("bunny", 10)):
         g1, g2 = frames[f"{name}_1"], frames[f"{name}_2"]
@@ -66,7 +79,7 @@ def main():
             fields[f"{name}_n{n}_{mode}_u"] = u[::4, ::4].copy()
             fields[f"{name}_n{n}_{mode}_v"] = v[::4, ::4].copy()
     np.savez_compressed(os.path.join(HERE, "fields.npz"), **fields)
-    for f in ("frames.npz", "masks.npz", "fields.npz"):
+    for f in ("frames.npz", "masks.npz", "pictures.npz", "fields.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

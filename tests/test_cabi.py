@@ -112,3 +112,36 @@ def test_stream_model_is_self_consistent(oracle, frames):
         u, v = M.sweep_direct(u, v, a, b, c, True)
     uo, vo = oracle.jacobi(Ex, Ey, Et, 15.0, 30, True)
     assert np.abs(u - uo).max() < 1e-5 and np.abs(v - vo).max() < 1e-5     # contract is 1e-3
+
+
+def test_host_rasteriser_equals_opencv_drawing(oracle, frames, pictures):
+    """hsimg_draw_flow (libhsflow_host.so: the drawing loop the drop-in classes run, cpp:758-770 / cv.cpp:32-46) against
+    cv2.circle + cv2.line: every pixel equal on the reference's own pictures and on random fields with flows of hundreds
+    of pixels (lines clipped at all four borders).  Host code only: no GPU needed."""
+    pytest.importorskip("cv2")
+    import ctypes as C
+    import numpy as np
+    from opticalflowhs_b200 import build_host
+    build_host.build()
+    L = C.CDLL(os.path.join(ROOT, "opticalflowhs_b200", "libhsflow_host.so"))
+    L.hsimg_draw_flow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+
+    def ours(u, v, thr, scale):
+        u, v = np.ascontiguousarray(u, np.float32), np.ascontiguousarray(v, np.float32)
+        out = np.zeros(u.shape + (3,), np.uint8)
+        assert L.hsimg_draw_flow(u.ctypes.data, v.ctypes.data, u.shape[1], u.shape[0], thr, scale, out.ctypes.data) == 0
+        return out
+
+    g1, g2 = frames["bunny_1"], frames["bunny_2"]
+    u, v = oracle.run_cl(g1, g2, 15.0, 10, False)
+    assert (oracle.jpeg_roundtrip(ours(u, v, 0.5, 1.0)) == pictures["bunny_cl_a15_n10"]).all()
+    u, v, _ = oracle.run_cv(g1, g2, 0.1, 10, eps=1e-6)
+    assert (oracle.jpeg_roundtrip(ours(u, v, 1.0, 0.5)) == pictures["bunny_cv_l0.1_n10"]).all()
+    rng = np.random.default_rng(0)
+    for _ in range(120):
+        h, w = int(rng.integers(5, 60)), int(rng.integers(5, 80))
+        keep = rng.random((h, w)) < 0.15
+        u = (rng.standard_normal((h, w)) * rng.choice([1, 5, 30, 200]) * keep).astype(np.float32)
+        v = (rng.standard_normal((h, w)) * rng.choice([1, 5, 30, 200]) * keep).astype(np.float32)
+        for thr, scale in ((0.5, 1.0), (1.0, 0.5)):
+            assert (ours(u, v, thr, scale) == oracle.render_flow(u, v, thr, scale)).all(), (h, w)

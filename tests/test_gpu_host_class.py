@@ -59,6 +59,47 @@ def test_unchanged_main_cl_disk_reproduces_shipped_pictures(tmp_path, frames, ma
     assert iou(m, masks[f"{name}_cl_a15_n{n}"]) == 1.0     # the class defaults to the shipped (LITERAL) kernel semantics
 
 
+@pytest.mark.skipif(not os.path.exists(EXE), reason="reference main.cpp binary not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name,n", [("city", 10), ("bunny", 10), ("bunny", 2)])
+def test_unchanged_main_writes_the_shipped_picture_pixel_for_pixel(tmp_path, oracle, frames, pictures, name, n):
+    """End to end through the reference's unchanged main.cpp: the picture our class writes, saved as JPEG at cvSaveImage's
+    default quality and loaded again, IS the shipped *_cl_out.jpg -- every pixel (threshold decisions, circles, line end
+    points trunc(x + u) of all grid points).  Bit-exact arithmetic (HSFLOW_EXACT=1) must hit it exactly; the default FAST
+    arithmetic (fields within 4e-6 px) is allowed a handful of end points that sit on an integer boundary."""
+    pytest.importorskip("cv2")
+    write_pgm(tmp_path / "a.pgm", frames[f"{name}_1"])
+    write_pgm(tmp_path / "b.pgm", frames[f"{name}_2"])
+    gold = pictures[f"{name}_cl_a15_n{n}"]
+    for env, budget in (({"HSFLOW_EXACT": "1"}, 0), ({}, 60)):
+        r = run_main(["-cl", "-hd", "a.pgm", "b.pgm", "out.ppm", "15", str(n), "1", "GPU"], tmp_path, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        bgr = np.ascontiguousarray(read_ppm(tmp_path / "out.ppm")[..., ::-1])
+        if budget == 0:
+            assert (oracle.jpeg_roundtrip(bgr) == gold).all()
+        else:
+            u, v = oracle.run_cl(frames[f"{name}_1"], frames[f"{name}_2"], 15.0, n, False)
+            assert (bgr != oracle.render_flow(u, v, 0.5, 1.0)).any(axis=2).sum() <= budget
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="reference main.cpp binary not built")
+@pytest.mark.parametrize("name", ["city", "bunny"])
+def test_unchanged_main_cv_picture_against_the_shipped_one(tmp_path, oracle, frames, pictures, name):
+    """-cv -hd (OpticalFlowOpenCV::runFromImg, cv.cpp:7-52) with lambda = 0.1, 10 iterations: the restated
+    cvCalcOpticalFlowHS reproduces *_cv_out.jpg exactly (tests/test_oracle.py); the GPU path uses another (equally valid)
+    operation order, so a few of the ~1 000 - 2 000 line end points may fall on the other side of an integer."""
+    pytest.importorskip("cv2")
+    write_pgm(tmp_path / "a.pgm", frames[f"{name}_1"])
+    write_pgm(tmp_path / "b.pgm", frames[f"{name}_2"])
+    r = run_main(["-cv", "-hd", "a.pgm", "b.pgm", "out.ppm", ".1", "10"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    bgr = np.ascontiguousarray(read_ppm(tmp_path / "out.ppm")[..., ::-1])
+    u, v, _ = oracle.run_cv(frames[f"{name}_1"], frames[f"{name}_2"], 0.1, 10, eps=1e-6)
+    ref = oracle.render_flow(u, v, 1.0, 0.5)
+    assert (oracle.jpeg_roundtrip(ref) == pictures[f"{name}_cv_l0.1_n10"]).all()
+    differing = (bgr != ref).any(axis=2).sum()
+    assert differing <= 120, differing                      # out of 288 000 / 101 760 pixels
+
+
 @pytest.mark.skipif(not os.path.exists(EXE), reason="reference main.cpp binary not built")
 def test_unchanged_main_cv_disk_and_error_paths(tmp_path, frames, masks):
     write_pgm(tmp_path / "a.pgm", frames["city_1"])

@@ -145,6 +145,44 @@ def test_golden_masks_literal_mode(eng, P, frames, masks, name, n, dots, math):
     assert not v.any()
 
 
+# ---- the shipped pictures through the GPU path, pixel for pixel ---------------------------------------------------
+
+@pytest.mark.parametrize("key,name,n", [("city_cl_a15_n10", "city", 10), ("bunny_cl_a15_n10", "bunny", 10), ("bunny_cl_a15_n2", "bunny", 2)])
+def test_shipped_cl_pictures_from_gpu_fields(eng, P, oracle, frames, pictures, key, name, n):
+    """The fields the GPU computes in LITERAL mode, drawn like cpp:758-770 and saved like cvSaveImage, ARE the shipped
+    *_cl_out.jpg: every pixel in EXACT math; FAST math (streaming kernel) may move an end point that sits on an integer."""
+    pytest.importorskip("cv2")
+    g1, g2 = frames[f"{name}_1"], frames[f"{name}_2"]
+    eng.set_math(P.MATH_EXACT).set_params(15.0, n, P.STENCIL_CL8, False)
+    eng.load_pair(g1, g2).compute()
+    u, v = eng.read_uv()
+    assert (oracle.jpeg_roundtrip(oracle.render_flow(u, v, 0.5, 1.0)) == pictures[key]).all()
+    eng.set_math(P.MATH_FAST).set_params(15.0, n, P.STENCIL_CL8, False, 0)
+    eng.load_pair(g1, g2).compute()
+    uf, vf = eng.read_uv()
+    assert (oracle.render_flow(uf, vf, 0.5, 1.0) != oracle.render_flow(u, v, 0.5, 1.0)).any(axis=2).sum() <= 60
+
+
+@pytest.mark.parametrize("name", ["city", "bunny"])
+def test_shipped_cv_pictures_from_gpu_fields(eng, P, oracle, frames, pictures, name):
+    """OpenCV-mode path (blur, Sobel estimator, 4-neighbour stencil, lambda = 0.1, 10 iterations, eps 1e-6): the restated
+    cvCalcOpticalFlowHS is pinned pixel-exactly by *_cv_out.jpg; the GPU fields are within 1e-3 px of it, so their
+    picture may differ in a few line end points out of the ~1 000 - 2 000 drawn."""
+    pytest.importorskip("cv2")
+    g1, g2 = frames[f"{name}_1"], frames[f"{name}_2"]
+    uo, vo, _ = oracle.run_cv(g1, g2, 0.1, 10, eps=1e-6)
+    ref = oracle.render_flow(uo, vo, 1.0, 0.5)
+    assert (oracle.jpeg_roundtrip(ref) == pictures[f"{name}_cv_l0.1_n10"]).all()
+    for math in (P.MATH_EXACT, P.MATH_FAST):
+        eng.set_math(math).set_deriv(P.DERIV_CV).set_params(0.0, 10, P.STENCIL_CV4, True, 0).set_lambda(0.1).set_epsilon(1e-6)
+        eng.load_pair(g1, g2).compute()
+        u, v = eng.read_uv()
+        assert np.abs(u - uo).max() <= TOL_MAX and np.abs(v - vo).max() <= TOL_MAX
+        differing = (oracle.render_flow(u, v, 1.0, 0.5) != ref).any(axis=2).sum()
+        assert differing <= 120, (math, differing)
+    eng.set_deriv(P.DERIV_CL).set_epsilon(0.0)
+
+
 # ---- FAST math: north-star tolerance ------------------------------------------------------------
 
 @pytest.mark.parametrize("name", ["city", "bunny"])
