@@ -45,7 +45,11 @@ enum {
 enum {
     HSFLOW_MATH_FAST = 0,  /* normalised coefficients + FMA; |du|,|dv| <= 1e-3 px vs the oracle   */
     HSFLOW_MATH_EXACT = 1  /* operand-for-operand Kernels.cl:55-63,84-86 without contraction and
-                              with IEEE division: bit-identical to the host oracle.  T = 1 only.  */
+                              with IEEE division: bit-identical to the host oracle.  T = 1 only.
+                              With HSFLOW_DERIV_CV + HSFLOW_STENCIL_CV4 the update follows the rounding
+                              sequence of cvCalcOpticalFlowHS instead (products xx, xy, yy, xt, yt and
+                              1 / (rho + xx + yy) per pixel): bit-identical to the restated routine that
+                              reproduces the shipped *_cv_out.jpg pixel for pixel.                    */
 };
 
 /* which derivative estimator feeds the iteration */

@@ -20,6 +20,8 @@ void hsflow_host_draw(std::vector<unsigned char>& img, int w, int h, const float
 static hsflow_t* cv_engine(float lambda, int it) {
     hsflow_t* e = NULL;
     if (hsflow_create(0, &e) != HSFLOW_OK) { std::cout << "hsflow: " << hsflow_last_error() << std::endl; return NULL; }
+    const char* ex = getenv("HSFLOW_EXACT");                                // bit-exact arithmetic (one sweep per launch), as for the CL class
+    hsflow_set_math(e, (ex && atoi(ex)) ? HSFLOW_MATH_EXACT : HSFLOW_MATH_FAST);
     hsflow_set_deriv(e, HSFLOW_DERIV_CV);                                   // cvSmooth x2 + Sobel estimator (cv.cpp:27-29)
     hsflow_set_params(e, 0.f, it, HSFLOW_STENCIL_CV4, 1, 0);
     hsflow_set_lambda(e, lambda);

@@ -115,6 +115,19 @@ __device__ __forceinline__ void update_exact(float ub, float vb, float ex, float
     vn = __fsub_rn(vb, __fmul_rn(ey, t));
 }
 
+// cvCalcOpticalFlowHS (OpenCV 2.1, restated in oracle/hs_oracle.c hso_cvhs from the disassembly), operand for
+// operand: products xx, xy, yy, xt, yt and a = 1 / (rho + xx + yy) as the routine stores them per pixel, then
+//   u' = ubar - (xx ubar + xy vbar + xt) a ,  v' = vbar - (xy ubar + yy vbar + yt) a
+// Mathematically the update above; numerically another rounding sequence.  The restated routine reproduces the shipped
+// *_cv_out.jpg pixel for pixel, so this is the form the EXACT OpenCV-mode path uses.
+__device__ __forceinline__ void update_exact_cv(float ub, float vb, float ix, float iy, float it, float rho, float& un, float& vn) {
+    const float xx = __fmul_rn(ix, ix), xy = __fmul_rn(ix, iy), yy = __fmul_rn(iy, iy);
+    const float xt = __fmul_rn(ix, it), yt = __fmul_rn(iy, it);
+    const float a = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(rho, xx), yy));
+    un = __fsub_rn(ub, __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(xx, ub), __fmul_rn(xy, vb)), xt), a));
+    vn = __fsub_rn(vb, __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(xy, ub), __fmul_rn(yy, vb)), yt), a));
+}
+
 // ---- clamp-to-edge (Tex2D, Kernels.cl:2-9) inside a lane-of-4 layout ------------------------
 // c[] holds columns col0..col0+3.  Make out-of-image columns replicate the edge column so
 // that the W/E taps read clamped values; l/r are the neighbours fetched by shuffle.

@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(128) k_jacobi1(Jacobi1Args A) {
                                nb(um, j - 1), nb(um, j + 1), nb(up, j - 1), nb(up, j + 1));
                 vb = avg_exact(we, wd, nb(v0, j - 1), nb(v0, j + 1), vm.c[j], vp.c[j],
                                nb(vm, j - 1), nb(vm, j + 1), nb(vp, j - 1), nb(vp, j + 1));
-                update_exact(ub, vb, ka[j], kb[j], kc[j], A.rho, un[j], vn[j]);
+                if (A.cv_form) update_exact_cv(ub, vb, ka[j], kb[j], kc[j], A.rho, un[j], vn[j]);
+                else update_exact(ub, vb, ka[j], kb[j], kc[j], A.rho, un[j], vn[j]);
             } else {
                 const float hum = __fadd_rn(nb(um, j - 1), nb(um, j + 1));
                 const float hu0 = __fadd_rn(nb(u0, j - 1), nb(u0, j + 1));

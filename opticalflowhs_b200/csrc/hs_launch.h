@@ -37,6 +37,7 @@ struct Jacobi1Args {
     int out_lo, out_hi;         // rows to produce
     int chunk_rows;
     float rho;                  // EXACT only
+    int cv_form;                // EXACT only: 1 = the operation order of cvCalcOpticalFlowHS (update_exact_cv), 0 = Kernels.cl:84-86
     // Convergence tracking (hsflow_set_epsilon; the CV_TERMCRIT_EPS half of cv.cpp:29), nullptr = off.
     // emax[pair]: max |new - old| of this sweep as float bits (atomicMax; non-negative floats order like uints).
     // stop[pair]: 0 = still iterating, else (sweeps executed << 1) | parity of the buffer that holds the field.

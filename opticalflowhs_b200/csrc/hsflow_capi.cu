@@ -774,6 +774,9 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
         A.chunk_rows = (int)std::max<long long>(1, std::min<long long>(rows, std::max<long long>(lo, std::min<long long>(64, fit))));
     }
     A.rho = h->rho;
+    // EXACT OpenCV-mode path: the rounding sequence of cvCalcOpticalFlowHS, so that the field is bit-identical to the
+    // restated routine the shipped *_cv_out.jpg pin
+    A.cv_form = (h->math == HSFLOW_MATH_EXACT && h->deriv == HSFLOW_DERIV_CV && h->stencil == HSFLOW_STENCIL_CV4) ? 1 : 0;
     if (h->ec_on) {                                // EPS mode: track max |new - old|, carry converged pairs over
         A.emax = h->d_emax + h->ec_off; A.stop = h->d_stop + h->ec_off;
         A.last_sweep = h->ec_sweep == h->ec_total; A.total_sweeps = h->ec_total;

@@ -85,19 +85,25 @@ def test_unchanged_main_writes_the_shipped_picture_pixel_for_pixel(tmp_path, ora
 @pytest.mark.parametrize("name", ["city", "bunny"])
 def test_unchanged_main_cv_picture_against_the_shipped_one(tmp_path, oracle, frames, pictures, name):
     """-cv -hd (OpticalFlowOpenCV::runFromImg, cv.cpp:7-52) with lambda = 0.1, 10 iterations: the restated
-    cvCalcOpticalFlowHS reproduces *_cv_out.jpg exactly (tests/test_oracle.py); the GPU path uses another (equally valid)
-    operation order, so a few of the ~1 000 - 2 000 line end points may fall on the other side of an integer."""
+    cvCalcOpticalFlowHS reproduces *_cv_out.jpg exactly (tests/test_oracle.py).  With HSFLOW_EXACT=1 the GPU follows its
+    rounding sequence and the picture main writes is the shipped one, pixel for pixel; the default FAST arithmetic may
+    put a few of the ~1 000 - 2 000 line end points on the other side of an integer."""
     pytest.importorskip("cv2")
     write_pgm(tmp_path / "a.pgm", frames[f"{name}_1"])
     write_pgm(tmp_path / "b.pgm", frames[f"{name}_2"])
-    r = run_main(["-cv", "-hd", "a.pgm", "b.pgm", "out.ppm", ".1", "10"], tmp_path)
-    assert r.returncode == 0, r.stdout + r.stderr
-    bgr = np.ascontiguousarray(read_ppm(tmp_path / "out.ppm")[..., ::-1])
     u, v, _ = oracle.run_cv(frames[f"{name}_1"], frames[f"{name}_2"], 0.1, 10, eps=1e-6)
     ref = oracle.render_flow(u, v, 1.0, 0.5)
-    assert (oracle.jpeg_roundtrip(ref) == pictures[f"{name}_cv_l0.1_n10"]).all()
-    differing = (bgr != ref).any(axis=2).sum()
-    assert differing <= 120, differing                      # out of 288 000 / 101 760 pixels
+    gold = pictures[f"{name}_cv_l0.1_n10"]
+    assert (oracle.jpeg_roundtrip(ref) == gold).all()
+    for env in ({"HSFLOW_EXACT": "1"}, {}):
+        r = run_main(["-cv", "-hd", "a.pgm", "b.pgm", "out.ppm", ".1", "10"], tmp_path, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        bgr = np.ascontiguousarray(read_ppm(tmp_path / "out.ppm")[..., ::-1])
+        if env:                                             # rounding sequence of cvCalcOpticalFlowHS: the shipped picture, every pixel
+            assert (oracle.jpeg_roundtrip(bgr) == gold).all()
+        else:
+            differing = (bgr != ref).any(axis=2).sum()
+            assert differing <= 120, differing              # out of 288 000 / 101 760 pixels
 
 
 @pytest.mark.skipif(not os.path.exists(EXE), reason="reference main.cpp binary not built")

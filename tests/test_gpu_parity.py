@@ -166,8 +166,9 @@ def test_shipped_cl_pictures_from_gpu_fields(eng, P, oracle, frames, pictures, k
 @pytest.mark.parametrize("name", ["city", "bunny"])
 def test_shipped_cv_pictures_from_gpu_fields(eng, P, oracle, frames, pictures, name):
     """OpenCV-mode path (blur, Sobel estimator, 4-neighbour stencil, lambda = 0.1, 10 iterations, eps 1e-6): the restated
-    cvCalcOpticalFlowHS is pinned pixel-exactly by *_cv_out.jpg; the GPU fields are within 1e-3 px of it, so their
-    picture may differ in a few line end points out of the ~1 000 - 2 000 drawn."""
+    cvCalcOpticalFlowHS is pinned pixel-exactly by *_cv_out.jpg.  EXACT math follows its rounding sequence: bit-identical
+    fields, so the GPU's picture is the shipped one pixel for pixel.  FAST math is within 1e-3 px, so its picture may
+    differ in a few line end points out of the ~1 000 - 2 000 drawn."""
     pytest.importorskip("cv2")
     g1, g2 = frames[f"{name}_1"], frames[f"{name}_2"]
     uo, vo, _ = oracle.run_cv(g1, g2, 0.1, 10, eps=1e-6)
@@ -178,8 +179,12 @@ def test_shipped_cv_pictures_from_gpu_fields(eng, P, oracle, frames, pictures, n
         eng.load_pair(g1, g2).compute()
         u, v = eng.read_uv()
         assert np.abs(u - uo).max() <= TOL_MAX and np.abs(v - vo).max() <= TOL_MAX
-        differing = (oracle.render_flow(u, v, 1.0, 0.5) != ref).any(axis=2).sum()
-        assert differing <= 120, (math, differing)
+        if math == P.MATH_EXACT:                    # the rounding sequence of cvCalcOpticalFlowHS: bit-identical, so the picture is too
+            assert (bits(u) == bits(uo)).all() and (bits(v) == bits(vo)).all()
+            assert (oracle.jpeg_roundtrip(oracle.render_flow(u, v, 1.0, 0.5)) == pictures[f"{name}_cv_l0.1_n10"]).all()
+        else:
+            differing = (oracle.render_flow(u, v, 1.0, 0.5) != ref).any(axis=2).sum()
+            assert differing <= 120, (math, differing)
     eng.set_deriv(P.DERIV_CL).set_epsilon(0.0)
 
 
@@ -739,8 +744,9 @@ def test_bench_geometry_batch_windows_against_oracle_crops(P, oracle):
 def test_baseline_config1_bunny_cv_path_as_written(P, oracle, frames):
     """BASELINE.json configs[0] exactly as the reference runs it (main.cpp:4, 8, 20; OpticalFlowOpenCV.cpp:27-29): the bunny
     pair, lambda = 0.1, 100 iterations, cvTermCriteria(ITER | EPS, 100, 1e-6), both 3x3 blurs.  The comparator is the
-    restated cvCalcOpticalFlowHS (parity-unpinned: cv210.dll's source is not in the reference tree), so this is the
-    looser cross-check: field within 1e-3 px; in EXACT math the sweep count is equal too."""
+    restated cvCalcOpticalFlowHS (cv210.dll's source is not in the reference tree; the restatement is pinned pixel-exactly
+    by the shipped *_cv_out.jpg, tests/test_oracle.py): EXACT math bit-identical in field and sweep count, FAST math within
+    1e-3 px."""
     g1, g2 = frames["bunny_1"], frames["bunny_2"]
     uo, vo, it = oracle.run_cv(g1, g2, 0.1, 100, eps=1e-6)
     for math in (P.MATH_EXACT, P.MATH_FAST):
@@ -753,6 +759,7 @@ def test_baseline_config1_bunny_cv_path_as_written(P, oracle, frames):
         assert epe_diff(u, v, uo, vo) <= TOL_EPE
         if math == P.MATH_EXACT:
             assert done == it
+            assert (bits(u) == bits(uo)).all() and (bits(v) == bits(vo)).all()
         else:
             assert abs(done - it) <= 1 or done == it == 100
 
