@@ -15,6 +15,13 @@ A "step" is one pass of the hot path (derivatives + 100 iterations) over the ran
   roofline  dominant kernel k_jacobi_stream<T>: algorithmic (unfused-equivalent) bytes
             28 B x pixels x T per launch / launch time measured with CUDA events inside the timed
             region (iteration phase of the last timed step / launches), against MEASURED_PEAKS.json
+  parity    windows of the first and the last pair of the TIMED batch against the oracle on their domains of
+            dependence (after the timed region; max |du|, |dv| in px); e2e.parity the same for the host-buffer path
+  e2e.wire  plain pinned cudaMemcpyAsync copies on every rank at the same time, measured in the same run: the box's own
+            ceiling for the 8 B/px of results (e2e.wire_bound_value, e2e.frac_of_wire_bound)
+  e2e.sampled  the same call returning only the stride-4 samples of u, v the reference's consumer reads (cpp:762-767)
+  strip16k  BASELINE.json configs[4] as a sub-record of every line: one 16384 x 16384 pair, 500 iterations, row strips
+            over the N GPUs with the fused peer transport, window on the GPU seam checked against the oracle
   cpu_baseline / --impl reference: the reference's own Kernels.cl compiled for the host
             (oracle/_ref/libclref.so, OpenMP over rows = what its CL_DEVICE_TYPE_CPU path does),
             bounded sample, on the box's host cores.  oracle/ is only ever the thing timed here,
