@@ -202,6 +202,12 @@ int hsflow_run_sequence_host(hsflow_t* h, const uint8_t* frames, int n_frames, i
 enum { HSFLOW_PIPE_SEQUENCE = 1 };
 int hsflow_run_pipeline_host(hsflow_t* h, const uint8_t* frames, int n_pairs, int w, int hgt, int frame_format, int flags,
                              int sample_step, float* u_out, float* v_out);
+/* The same over several handles at once -- usually one per GPU of the box: pair k goes to handle k / ceil(n_pairs /
+ * n_handles) (contiguous blocks), every handle runs its block on its own host thread, no data crosses
+ * between GPUs.  The reference owns exactly one device (cpp:158 devices[0]); this is its batch loop over all of them.
+ * The caller creates the handles (hsflow_create(device_k, ..)) and sets the same parameters on each. */
+int hsflow_run_pipeline_host_multi(hsflow_t* const* handles, int n_handles, const uint8_t* frames, int n_pairs, int w, int hgt,
+                                   int frame_format, int flags, int sample_step, float* u_out, float* v_out);
 /* Streaming form for a handle configured with one pair: the current second frame becomes the first
  * (pointer swap in HBM), `frame` is uploaded as the new second frame; then hsflow_compute as usual.
  * The very first frame pushed fills both planes (zero flow). */

@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <unistd.h>
@@ -1476,6 +1478,41 @@ int hsflow_run_pipeline_host(hsflow_t* h, const uint8_t* frames, int n_pairs, in
     if (flags & ~HSFLOW_PIPE_SEQUENCE) return fail(HSFLOW_EINVAL, "unknown pipeline flags 0x%x", flags);
     const int fmt = frame_format == HSFLOW_FRAMES_GRAY8 ? FMT_GRAY8 : (frame_format == HSFLOW_FRAMES_BGR8 ? FMT_BGR8 : -1);
     return run_pipeline(h, frames, n_pairs, w, hgt, u_out, v_out, PipeOpts{fmt, (flags & HSFLOW_PIPE_SEQUENCE) ? 1 : 0, sample_step});
+}
+
+// Pair sharding inside one process (independent frame pairs, contiguous blocks of ceil(P / n) pairs per GPU, no
+// data-path collective): one host thread per handle runs the pipelined call on its block.  The handles usually live on
+// different GPUs; the caller created them and set their parameters.
+int hsflow_run_pipeline_host_multi(hsflow_t* const* handles, int n_handles, const uint8_t* frames, int n_pairs, int w, int hgt,
+                                   int frame_format, int flags, int sample_step, float* u_out, float* v_out) {
+    if (!handles || n_handles <= 0) return fail(HSFLOW_EINVAL, "no handles");
+    for (int k = 0; k < n_handles; ++k) if (!handles[k]) return fail(HSFLOW_EINVAL, "null handle");
+    if (!frames || !u_out || !v_out || n_pairs <= 0 || w <= 0 || hgt <= 0) return fail(HSFLOW_EINVAL, "bad argument");
+    if (flags & ~HSFLOW_PIPE_SEQUENCE) return fail(HSFLOW_EINVAL, "unknown pipeline flags 0x%x", flags);
+    if (sample_step < 0) return fail(HSFLOW_EINVAL, "sample_step must be >= 0");
+    const int fmt = frame_format == HSFLOW_FRAMES_GRAY8 ? FMT_GRAY8 : (frame_format == HSFLOW_FRAMES_BGR8 ? FMT_BGR8 : -1);
+    if (fmt < 0) return fail(HSFLOW_EINVAL, "frame format must be gray8 or bgr8");
+    const int seq = (flags & HSFLOW_PIPE_SEQUENCE) ? 1 : 0;
+    const size_t fbytes = (size_t)w * hgt * (fmt == FMT_BGR8 ? 3 : 1);
+    const size_t opx = sample_step ? (size_t)((w + sample_step - 1) / sample_step) * ((hgt + sample_step - 1) / sample_step) : (size_t)w * hgt;
+    const int per = (n_pairs + n_handles - 1) / n_handles;
+    std::vector<int> rc((size_t)n_handles, HSFLOW_OK);
+    std::vector<std::string> msg((size_t)n_handles);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n_handles; ++k) {
+        const int lo = std::min(k * per, n_pairs), hi = std::min(lo + per, n_pairs);
+        if (lo >= hi) continue;
+        th.emplace_back([&, k, lo, hi] {
+            const uint8_t* f = frames + (size_t)lo * (seq ? 1 : 2) * fbytes;      // a sequence block starts at its first frame
+            rc[(size_t)k] = run_pipeline(handles[k], f, hi - lo, w, hgt, u_out + (size_t)lo * opx, v_out + (size_t)lo * opx,
+                                         PipeOpts{fmt, seq, sample_step});
+            if (rc[(size_t)k]) msg[(size_t)k] = g_err;                              // g_err is thread-local: carry it out
+        });
+    }
+    for (std::thread& t : th) t.join();
+    for (int k = 0; k < n_handles; ++k)
+        if (rc[(size_t)k]) return fail(rc[(size_t)k], "handle %d: %s", k, msg[(size_t)k].c_str());
+    return HSFLOW_OK;
 }
 
 // Camera-loop step on the device (cpp:800-842): the second frame of the handle's pair becomes the first one (cpp:834

@@ -78,6 +78,7 @@ SIGNATURES = {
     "hsflow_run_batch_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hsflow_run_pipeline_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hsflow_run_sequence_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "hsflow_run_pipeline_host_multi": (C.c_int, [C.POINTER(_P), C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hsflow_push_frame_gray8": (C.c_int, [_P, _P, C.c_size_t]),
     "hsflow_last_ms": (C.c_float, [_P, C.c_int]),
     "hsflow_kernel_launches": (C.c_longlong, [_P]),
@@ -335,6 +336,27 @@ class HSFlow:
         self._after_pipeline(W, H)
         self._ck(rc)
         return self
+
+    @staticmethod
+    def run_pipeline_host_multi(engines, frames, u_out, v_out, sequence=False, sample_step=0):
+        """run_pipeline_host over several handles (one per GPU): contiguous blocks of pairs, one host thread per handle."""
+        e0 = engines[0]
+        frames = e0._host_array(frames, np.uint8, "frames")
+        lead = 1 if sequence else 2
+        bgr = frames.ndim == lead + 3
+        n = frames.shape[0] - 1 if sequence else frames.shape[0]
+        H, W = frames.shape[lead], frames.shape[lead + 1]
+        oshape = (n, -(-H // sample_step), -(-W // sample_step)) if sample_step else (n, H, W)
+        for a, what in ((u_out, "u_out"), (v_out, "v_out")):
+            e0._host_array(a, np.float32, what)
+            if a.shape != oshape:
+                raise ValueError(f"{what} must have shape {oshape}, got {a.shape}")
+        hs = (_P * len(engines))(*[e._h for e in engines])
+        rc = e0._L.hsflow_run_pipeline_host_multi(hs, len(engines), _ptr(frames), n, W, H, FRAMES_BGR8 if bgr else FRAMES_GRAY8,
+                                                  PIPE_SEQUENCE if sequence else 0, int(sample_step), _ptr(u_out), _ptr(v_out))
+        for e in engines:
+            e._after_pipeline(W, H)
+        e0._ck(rc)
 
     def sample_uv(self, pair=0, step=4):
         """u, v on the stride-`step` grid (what cpp:762-767 reads)."""

@@ -399,6 +399,39 @@ def test_pipelined_bgr_frames_and_sampled_fields(P, oracle, sequence):
                 assert (bits(vs[k]) == bits(want[k][1][::step, ::step])).all(), (step, k)
 
 
+@pytest.mark.parametrize("sequence", [False, True])
+def test_pipeline_over_several_handles_equals_one_handle(P, oracle, sequence):
+    """hsflow_run_pipeline_host_multi: pair sharding inside one process (contiguous blocks of pairs, one host thread per
+    handle -- here three handles, spread over the GPUs that exist) against the single-handle call; ragged last block."""
+    import torch
+    W, H, n, N = 232, 64, 14, 11
+    nf = n + 1 if sequence else 2 * n
+    frames = np.stack([oracle.synth_pair(W, H, seed=300 + k)[k & 1] for k in range(nf)])
+    if not sequence:
+        frames = frames.reshape(n, 2, H, W)
+    u1, v1 = np.empty((n, H, W), np.float32), np.empty((n, H, W), np.float32)
+    with P.HSFlow(0) as e:
+        e.set_params(15.0, N, P.STENCIL_CL8, True, 4)
+        e.run_pipeline_host(frames, u1, v1, sequence=sequence)
+    ndev = torch.cuda.device_count()
+    engs = [P.HSFlow(k % ndev) for k in range(3)]
+    try:
+        for e in engs:
+            e.set_params(15.0, N, P.STENCIL_CL8, True, 4).set_tuning(sub_batch=2)
+        for step in (0, 4):
+            shape = (n, -(-H // step), -(-W // step)) if step else (n, H, W)
+            u, v = np.empty(shape, np.float32), np.empty(shape, np.float32)
+            P.HSFlow.run_pipeline_host_multi(engs, frames, u, v, sequence=sequence, sample_step=step)
+            ru, rv = (u1[:, ::step, ::step], v1[:, ::step, ::step]) if step else (u1, v1)
+            assert (bits(u) == bits(ru)).all() and (bits(v) == bits(rv)).all(), step
+        with pytest.raises(P.HSFlowError):              # an error inside one block comes out with its handle's message
+            engs[1].set_strip(False, True)
+            P.HSFlow.run_pipeline_host_multi(engs, frames, u, v, sequence=sequence, sample_step=4)
+    finally:
+        for e in engs:
+            e.close()
+
+
 def test_compute_range_on_pair_slots_and_frames_written_on_the_device(P, oracle):
     """hsflow_compute_range (two halves of the pair slots computed independently -- what the JPEG ingest uses to overlap
     decode and compute) and the device-side frame entries hsflow_map_frames / hsflow_set_frames_*_dev, against per-pair
