@@ -77,14 +77,6 @@ struct StreamArgs {
     unsigned* flag_up;          // word in the upper / lower neighbour's memory that receives `epoch`
     unsigned* flag_dn;
     unsigned epoch;
-    // In-kernel seam wait (neighbours on OTHER devices, seam_first launches only): instead of a stream wait between
-    // every two launches, the units of the top row chunk wait here until the upper neighbour published epoch - 1 in
-    // *wait_up (its seam rows for this launch are in our source buffer and it no longer reads the rows we are about
-    // to push), the units of the bottom chunk likewise on *wait_dn; interior units touch neither ghost rows nor
-    // neighbours and start at once.  Launches then follow each other without a stream-level dependency and overlap
-    // through programmatic dependent launch.  nullptr = no wait (the stream already waited).
-    const unsigned* wait_up;
-    const unsigned* wait_dn;
     // EPS criterion on the temporally blocked kernel (TRACK instantiation; cvTermCriteria(ITER | EPS), cv.cpp:29).
     // A block of trk_t <= T sweeps runs as TWO launches over the same source and destination buffers:
     //   main   (trk_mode 0): pairs that are still iterating run all trk_t sweeps; every stage S reduces

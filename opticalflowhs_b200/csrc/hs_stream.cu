@@ -88,8 +88,6 @@ cudaError_t launch_jacobi_stream(int T, int stencil, const CUtensorMap& tuv, con
     if (stream_seam_first(T, A)) {
         A.seam_first = 1;
         A.signal_units = (long long)A.nsx * 2 * pairs;
-    } else {
-        A.wait_up = A.wait_dn = nullptr;               // the in-kernel seam wait needs the seam-first order
     }
     const bool peer = A.done_counter != nullptr;    // strip connected to its neighbours (hsflow_strip_connect)
     switch (T) {

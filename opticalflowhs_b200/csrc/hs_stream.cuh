@@ -160,13 +160,32 @@ template <int T> struct DefaultCfg {
 #define HS_COEF_Z(z) (z)
 #endif
 
+// Peer store of one output row (row strips over several GPUs): rows a neighbour keeps as ghost rows are stored a second
+// time, straight into that neighbour's destination buffer over NVLink.  Deliberately NOT inlined and fed through a pointer
+// to the kernel's (grid-constant) argument block: inlined, the compiler hoists the address arithmetic out of the tick
+// loop and keeps eight more registers alive through the steady-state loop, which at T = 6 means spills and 10 % more
+// instructions for every unit of the launch.  Only the few ticks at a strip seam ever call it.
+static __device__ __noinline__ void peer_push_row(const StreamArgs* __restrict__ Ap, int ro, int col0, float4 u, float4 v) {
+    const long long voff = Ap->v_out - Ap->u_out;
+    if (Ap->peer_up != nullptr && ro >= Ap->up_lo && ro < Ap->up_hi) {
+        float* q = Ap->peer_up + (size_t)(ro + Ap->up_delta) * Ap->row_pitch + col0;
+        *reinterpret_cast<float4*>(q) = u;
+        *reinterpret_cast<float4*>(q + voff) = v;
+    }
+    if (Ap->peer_dn != nullptr && ro >= Ap->dn_lo && ro < Ap->dn_hi) {
+        float* q = Ap->peer_dn + (size_t)(ro + Ap->dn_delta) * Ap->row_pitch + col0;
+        *reinterpret_cast<float4*>(q) = u;
+        *reinterpret_cast<float4*>(q + voff) = v;
+    }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------
 #ifndef HS_STREAM_MIN_CTAS
 #define HS_STREAM_MIN_CTAS 1     // experiments: 3 caps the kernel at 168 registers (12 warps per SM)
 #endif
 template <int T, int ST, bool PEER, bool TRACK = false>
 __global__ void __launch_bounds__(32, HS_STREAM_MIN_CTAS)
-k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant__ CUtensorMap tm_c, const StreamArgs A) {
+k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ StreamArgs A) {
     using C = typename DefaultCfg<T>::type;
     constexpr int RG = C::RG, NGC = C::NGC, NGUV = C::NGUV, DRET = C::DRET;
     constexpr int NRC = C::NRC, NRUV = C::NRUV, ROWB = C::ROWB;
@@ -192,7 +211,6 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     int cy = (int)(tt % A.ncy);
     const int z = (int)(tt / A.ncy);
     if (PEER && A.seam_first && A.ncy > 2) cy = cy == 0 ? 0 : (cy == 1 ? A.ncy - 1 : cy - 1);   // seam chunks run first
-    const bool counted = !PEER || !A.seam_first || cy == 0 || cy == A.ncy - 1;
     const int W = A.W, H = A.H;
     const int R0 = A.out_lo + cy * A.chunk_rows;
     const int R1 = min(R0 + A.chunk_rows, A.out_hi);
@@ -260,32 +278,6 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             if (lane == 0) A.stop[zt] = ((A.trk_base + lim) << 1) | A.trk_dst_parity;   // every unit of the pair writes the same word
         }
     }
-    if constexpr (PEER) {
-        // In-kernel seam wait (StreamArgs::wait_up / wait_dn): only the units of the top and bottom row chunks read
-        // ghost rows and push seam rows; they wait until the neighbour on their side published the previous epoch.
-        // The neighbour runs on another GPU and never waits for THIS launch, so the wait cannot cycle.
-        const unsigned* w = !A.seam_first ? nullptr : (cy == 0 ? A.wait_up : (cy == A.ncy - 1 ? A.wait_dn : nullptr));
-        if (w != nullptr) {
-            if (lane == 0) {
-                const unsigned need = A.epoch - 1u;
-                auto seen = [&]() {
-                    unsigned x;
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(w) : "memory");
-                    return x;
-                };
-                if ((int)(seen() - need) < 0) {
-                    const uint64_t t0 = globaltimer_ns();
-                    while ((int)(seen() - need) < 0) {
-                        __nanosleep(200);
-                        if (globaltimer_ns() - t0 > 3 * kMbarTimeoutNs) __trap();   // a neighbour that never comes: fail loudly
-                    }
-                }
-                // the neighbour's rows were written through the generic proxy; this unit reads them with TMA
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
-            __syncwarp();
-        }
-    }
     if (lane == 0) {
         // A slot whose first box arrives in an odd virtual round gets one empty phase up front, so that
         // "parity = round & 1" holds for every slot.
@@ -344,23 +336,6 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     // Peer transport (row strips over several GPUs): rows a neighbour keeps as ghost rows are stored a second time,
     // straight into that neighbour's destination buffer over NVLink.  Decided per chunk: only the units at the top
     // and bottom of the strip ever take the branch.
-    const bool push_up = PEER && A.peer_up != nullptr && R0 < A.up_hi && R1 > A.up_lo;
-    const bool push_dn = PEER && A.peer_dn != nullptr && R0 < A.dn_hi && R1 > A.dn_lo;
-    const bool push_any = push_up || push_dn;
-    const long long voff = A.v_out - A.u_out;
-    auto push_row = [&](const int ro, const float (&cu)[4], const float (&cv)[4]) {
-        if (push_up && ro >= A.up_lo && ro < A.up_hi) {
-            float* q = A.peer_up + (size_t)(ro + A.up_delta) * A.row_pitch + col0;
-            *reinterpret_cast<float4*>(q) = make_float4(cu[0], cu[1], cu[2], cu[3]);
-            *reinterpret_cast<float4*>(q + voff) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-        }
-        if (push_dn && ro >= A.dn_lo && ro < A.dn_hi) {
-            float* q = A.peer_dn + (size_t)(ro + A.dn_delta) * A.row_pitch + col0;
-            *reinterpret_cast<float4*>(q) = make_float4(cu[0], cu[1], cu[2], cu[3]);
-            *reinterpret_cast<float4*>(q + voff) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-        }
-    };
-
     // time step S+1 of one row from its averages and coefficients (two packed pixel pairs per field)
     auto update_rows = [&](const f32x2 (&ub)[2], const f32x2 (&vb)[2], const float4& ka, const float4& kb, const float4& kc,
                            float (&cu)[4], float (&cv)[4]) {
@@ -506,7 +481,10 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
             const size_t o = (size_t)ro * A.row_pitch;
             *reinterpret_cast<float4*>(uo + o) = make_float4(cu[0], cu[1], cu[2], cu[3]);
             *reinterpret_cast<float4*>(vo + o) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            if constexpr (PEER) { if (push_any) push_row(ro, cu, cv); }
+            if constexpr (PEER) {
+                if ((A.peer_up != nullptr && ro < A.up_hi) || (A.peer_dn != nullptr && ro >= A.dn_lo))
+                    peer_push_row(&A, ro, col0, make_float4(cu[0], cu[1], cu[2], cu[3]), make_float4(cv[0], cv[1], cv[2], cv[3]));
+            }
         }
         // Ring refills, after every lane consumed its shared-memory reads of this tick:
         //  * the u/v group whose last row was read by stage 0 in this tick,
@@ -581,7 +559,8 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
                 if (orow + J < out_rows) {
                     *reinterpret_cast<float4*>(uo_row) = make_float4(cu[0], cu[1], cu[2], cu[3]);
                     *reinterpret_cast<float4*>(vo_row) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-                    if constexpr (PEER) { if (push_any) push_row(r + J - T, cu, cv); }
+                    // no peer stores here: the ticks whose output rows a neighbour keeps as ghosts run in tick_gen (see the
+                    // driver loop below), so that the steady state of a PEER launch is the steady state of any launch
                 }
                 uo_row += A.row_pitch; vo_row += A.row_pitch;
             };
@@ -618,7 +597,16 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
 
     int r = rs;
     int gen_end = min(fill_end, last_tick + 1);                  // pipeline fill (and tiny frames)
-    const int steady_end = min(H - 1, last_tick);                // last tick with a real input row
+    int steady_end = min(H - 1, last_tick);                      // last tick with a real input row
+    if constexpr (PEER) {
+        // Output row ro leaves at tick ro + T.  Rows [up_lo, up_hi) / [dn_lo, dn_hi) are also stored into a neighbour:
+        // those few ticks (T + 1 rows at the top of the first chunk, T at the bottom of the last one) stay in the
+        // generic path, which carries the push code; the branch-free loop in between carries none.  (With the push
+        // inside the steady loop every unit of a PEER launch paid 25 % more instructions per stage-row, and the seam
+        // units -- the slowest of a single-wave launch -- set its duration.)
+        if (A.peer_up != nullptr && R0 < A.up_hi && R1 > A.up_lo) gen_end = max(gen_end, min((A.up_hi + T + RG - 1) / RG * RG, last_tick + 1));
+        if (A.peer_dn != nullptr && R0 < A.dn_hi && R1 > A.dn_lo) steady_end = min(steady_end, A.dn_lo + T - 1);
+    }
     for (int pass = 0; pass < 2; ++pass) {
         for (; r < gen_end; ++r) tick_gen(r);
         if (pass == 1 || r > last_tick) break;
@@ -648,6 +636,11 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
     // counts itself done after its stores (local and peer) are visible system-wide; the last one resets the counter
     // and publishes the epoch to both neighbours, whose streams wait on that word (cuStreamWaitValue32) before they
     // launch the next block.  No kernel ever spins on it.
+    // (whether this unit counts is recomputed from blockIdx here instead of being kept alive through the pipeline)
+    bool counted = PEER;
+    if constexpr (PEER) {
+        if (A.seam_first && A.ncy > 2) { const int q = (int)((blockIdx.x / (unsigned)A.nsx) % (unsigned)A.ncy); counted = q < 2; }
+    }
     if (PEER && A.done_counter != nullptr && counted) {
         __syncwarp();
         if (lane == 0) {

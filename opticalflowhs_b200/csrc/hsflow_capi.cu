@@ -136,7 +136,6 @@ struct hsflow {
     int connected = 0;
     unsigned epoch = 0;
     unsigned waited_epoch = 0;                     // neighbours' epoch the stream has already waited for (cuStreamWaitValue32)
-    int seam_inkernel = 0;                         // all neighbours live on other devices: seam units wait in the kernel instead
     // EPS termination (hsflow_set_epsilon): per-pair device words, see Jacobi1Args
     double eps = 0.0;
     unsigned* d_emax = nullptr;
@@ -718,16 +717,12 @@ static int run_block(hsflow* h, int t, int src, int pA, int n, int out_lo, int o
             A.flag_up = h->has_peer[0] ? (unsigned*)h->peer[0][2] + 1 : nullptr;   // we are its lower neighbour
             A.flag_dn = h->has_peer[1] ? (unsigned*)h->peer[1][2] + 0 : nullptr;   // we are its upper neighbour
             A.epoch = h->epoch;
-            // This launch needs the neighbours' previous epoch.  Neighbours on other GPUs + seam chunks first: the seam
-            // units wait for it inside the kernel and the launch overlaps the tail of its predecessor (programmatic
-            // dependent launch).  Otherwise the stream waits.
-            if (h->seam_inkernel && stream_seam_first(t, A)) {
-                A.wait_up = h->has_peer[0] ? h->sig + 0 : nullptr;
-                A.wait_dn = h->has_peer[1] ? h->sig + 1 : nullptr;
-            } else {
-                int rc = strip_stream_wait(h, h->epoch - 1u);
-                if (rc) return rc;
-            }
+            // This launch needs the neighbours' previous epoch: the stream waits for it (no kernel ever spins).
+            // Tried in round 2 and removed: waiting inside the seam units of the kernel instead (ld.acquire.sys on the
+            // epoch word) so that launches overlap through programmatic dependent launch.  Bit-identical, but no faster on
+            // 2 x B200 (4.530 vs 4.544 ms per 120 iterations of 2048-row strips) and the spin loop cost the PEER
+            // instantiation 19 registers (236 -> 255 with spills at T = 6), which slowed every unit of the launch.
+            { int rc = strip_stream_wait(h, h->epoch - 1u); if (rc) return rc; }
         }
         if (h->ec_on) {                            // EPS criterion: main launch + replay launch on the TRACK instantiation
             if (h->connected || h->ov_u || t > kTrackT) return fail(HSFLOW_EINVAL, "internal: EPS block outside its envelope");
@@ -1134,24 +1129,6 @@ int hsflow_strip_connect(hsflow_t* h, const hsflow_strip_handle_t* up, int up_lo
     }
     h->top_edge = h->has_peer[0] ? 0 : 1;
     h->bottom_edge = h->has_peer[1] ? 0 : 1;
-    {
-        // Stream-level waits (cuStreamWaitValue32 between launches) are the default.  HSFLOW_STRIP_WAIT=kernel moves the
-        // wait into the seam units of the kernel so that launches overlap through programmatic dependent launch --
-        // allowed only when every neighbour runs on another GPU (kernels of one GPU must never wait for each other:
-        // nothing guarantees they run at the same time).  Measured on 2 x B200 with 2048-row and 8192-row strips: no
-        // difference (4.530 vs 4.544 ms per 120 iterations; 71.9 vs 72.2 ms per 500), because what a short strip loses
-        // is the lockstep fill and drain of its single wave of work units, not the hand-over between launches; the
-        // option stays for boxes where the stream wait is slower.
-        int other = 1;
-        for (int d = 0; d < 2; ++d) {
-            if (!blobs[d]) continue;
-            StripBlob b;
-            memcpy(&b, blobs[d], sizeof b);
-            if (b.device == h->device) other = 0;
-        }
-        const char* env = getenv("HSFLOW_STRIP_WAIT");
-        h->seam_inkernel = (env && !strcmp(env, "kernel") && other) ? 1 : 0;
-    }
     h->connected = 1;
     h->prepared = 0;
     return HSFLOW_OK;

@@ -23,8 +23,9 @@ W, ROWS, N, T = int(os.environ.get("W", 16384)), int(os.environ.get("ROWS", 2048
 SLICE, CHECK = int(os.environ.get("SLICE", 1)), int(os.environ.get("CHECK", 1))
 H = ROWS * G
 engs = [P.HSFlow(d) for d in range(G)]
+CHUNK = int(os.environ.get("CHUNK", 0))            # rows per work unit (0 = the engine's rule)
 for e in engs:
-    e.set_params(15.0, N, P.STENCIL_CL8, True, T)
+    e.set_params(15.0, N, P.STENCIL_CL8, True, T).set_tuning(chunk_rows=CHUNK)
 Teff = engs[0].temporal_block if T else 6
 s = LocalStripSolver(engs, W, H, Teff)
 s.load_synth(1234)
@@ -36,7 +37,7 @@ for _ in range(reps):
 s.sync()
 dt = (time.perf_counter() - t0) / reps
 out = {"gpus": G, "width": W, "height": H, "iterations": N, "temporal_block": engs[0].temporal_block, "ms": dt * 1e3,
-       "mpx_it_per_s": W * H * N / dt / 1e6, "slice_blocks": SLICE,
+       "mpx_it_per_s": W * H * N / dt / 1e6, "slice_blocks": SLICE, "chunk_rows": CHUNK,
        "seam_bytes_per_launch_per_direction": 2 * engs[0].temporal_block * W * 4,
        "launches_per_gpu": -(-N // engs[0].temporal_block)}
 if CHECK and H <= 8192:
