@@ -183,8 +183,13 @@ static __device__ __noinline__ void peer_push_row(const StreamArgs* __restrict__
 #ifndef HS_STREAM_MIN_CTAS
 #define HS_STREAM_MIN_CTAS 1     // experiments: 3 caps the kernel at 168 registers (12 warps per SM)
 #endif
+#ifdef HS_STREAM_MAXNREG           // experiments: cap the registers directly (e.g. 224 = nine warps per SM)
+#define HS_STREAM_BOUNDS __maxnreg__(HS_STREAM_MAXNREG)
+#else
+#define HS_STREAM_BOUNDS __launch_bounds__(32, HS_STREAM_MIN_CTAS)
+#endif
 template <int T, int ST, bool PEER, bool TRACK = false>
-__global__ void __launch_bounds__(32, HS_STREAM_MIN_CTAS)
+__global__ void HS_STREAM_BOUNDS
 k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ StreamArgs A) {
     using C = typename DefaultCfg<T>::type;
     constexpr int RG = C::RG, NGC = C::NGC, NGUV = C::NGUV, DRET = C::DRET;
