@@ -131,6 +131,7 @@ int decode_one(const uint8_t* jpeg, size_t len, uint8_t* d_bgr, size_t pitch, in
 // shared counter, run the host stage (nvjpegDecodeJpegHost) and queue the device stages (transfer, IDCT, colour
 // conversion straight into the destination plane) on their stream.
 struct Worker {
+    nvjpegHandle_t h = nullptr;                    // a library handle of its own: workers sharing one handle serialise inside nvJPEG
     nvjpegJpegDecoder_t dec = nullptr;
     nvjpegJpegState_t st = nullptr;
     nvjpegBufferPinned_t pin = nullptr;
@@ -140,7 +141,8 @@ struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     bool ok = false;
-    bool init(nvjpegHandle_t h) {
+    bool init() {
+        if (nvjpegCreateSimple(&h) != NVJPEG_STATUS_SUCCESS) return false;
         if (nvjpegDecoderCreate(h, NVJPEG_BACKEND_HYBRID, &dec) != NVJPEG_STATUS_SUCCESS) return false;
         if (nvjpegDecoderStateCreate(h, dec, &st) != NVJPEG_STATUS_SUCCESS) return false;
         if (nvjpegBufferPinnedCreate(h, nullptr, &pin) != NVJPEG_STATUS_SUCCESS) return false;
@@ -176,7 +178,6 @@ int pool_threads() {
 
 // returns HSFLOW_OK, or a negative code when the parallel path cannot take this batch (the caller falls back)
 int decode_parallel(const uint8_t* const* jpegs, const size_t* sizes, uint8_t* const* dsts, int n, size_t pitch) {
-    Decoder& D = dec();
     Pool& P = pool();
     const int want = std::min(pool_threads(), n);
     if (want < 2) return HSFLOW_EINVAL;
@@ -184,7 +185,7 @@ int decode_parallel(const uint8_t* const* jpegs, const size_t* sizes, uint8_t* c
         P.tried = true;
         cudaGetDevice(&P.device);
         P.w.resize((size_t)pool_threads());
-        for (Worker& wk : P.w) if (!wk.init(D.single)) { P.w.clear(); break; }
+        for (Worker& wk : P.w) if (!wk.init()) { P.w.clear(); break; }
     }
     if (P.w.empty()) return HSFLOW_EINVAL;
     std::atomic<int> next(0), failed(0);
@@ -196,10 +197,10 @@ int decode_parallel(const uint8_t* const* jpegs, const size_t* sizes, uint8_t* c
             nvjpegImage_t img;
             memset(&img, 0, sizeof img);
             img.channel[0] = dsts[i]; img.pitch[0] = pitch;
-            bool ok = nvjpegJpegStreamParse(D.single, jpegs[i], sizes[i], 0, 0, wk->js) == NVJPEG_STATUS_SUCCESS &&
-                      nvjpegDecodeJpegHost(D.single, wk->dec, wk->st, wk->par, wk->js) == NVJPEG_STATUS_SUCCESS &&
-                      nvjpegDecodeJpegTransferToDevice(D.single, wk->dec, wk->st, wk->js, wk->stream) == NVJPEG_STATUS_SUCCESS &&
-                      nvjpegDecodeJpegDevice(D.single, wk->dec, wk->st, &img, wk->stream) == NVJPEG_STATUS_SUCCESS;
+            bool ok = nvjpegJpegStreamParse(wk->h, jpegs[i], sizes[i], 0, 0, wk->js) == NVJPEG_STATUS_SUCCESS &&
+                      nvjpegDecodeJpegHost(wk->h, wk->dec, wk->st, wk->par, wk->js) == NVJPEG_STATUS_SUCCESS &&
+                      nvjpegDecodeJpegTransferToDevice(wk->h, wk->dec, wk->st, wk->js, wk->stream) == NVJPEG_STATUS_SUCCESS &&
+                      nvjpegDecodeJpegDevice(wk->h, wk->dec, wk->st, &img, wk->stream) == NVJPEG_STATUS_SUCCESS;
             // the state's pinned buffer is reused by the next image of this worker: its transfer has to be over
             if (ok) ok = cudaStreamSynchronize(wk->stream) == cudaSuccess;
             if (!ok) { failed.store(1); break; }
