@@ -145,3 +145,36 @@ def test_host_rasteriser_equals_opencv_drawing(oracle, frames, pictures):
         v = (rng.standard_normal((h, w)) * rng.choice([1, 5, 30, 200]) * keep).astype(np.float32)
         for thr, scale in ((0.5, 1.0), (1.0, 0.5)):
             assert (ours(u, v, thr, scale) == oracle.render_flow(u, v, thr, scale)).all(), (h, w)
+
+
+def test_stream_model_stage_limit_and_max_norm_tracking(oracle):
+    """The EPS criterion on the temporally blocked kernel, on the numpy model of its bookkeeping: a block whose stages
+    >= lim pass their input through equals exactly `lim` direct sweeps (tail blocks, replay launch), and the per-stage
+    max-norm over the rows a unit owns equals max |sweep s+1 - sweep s| there -- for chunks at the top, in the middle and
+    at the bottom of the frame (first-row replicate, virtual bottom row)."""
+    import numpy as np
+    import stream_model as M
+    f1, f2 = oracle.synth_pair(96, 40, seed=9)
+    Ex, Ey, Et = oracle.derivatives(f1.astype(np.float32), f2.astype(np.float32))
+    a, b, c = M.normalise(Ex, Ey, Et, 225.0)
+    rng = np.random.default_rng(2)
+    u0 = rng.standard_normal((40, 96)).astype(np.float32)
+    v0 = rng.standard_normal((40, 96)).astype(np.float32)
+    T = 4
+    direct = [(u0, v0)]
+    for _ in range(T):
+        direct.append(M.sweep_direct(direct[-1][0], direct[-1][1], a, b, c))
+    for (R0, R1) in ((0, 13), (13, 29), (29, 40), (0, 40)):
+        for lim in range(0, T + 1):
+            emax = [0.0] * T
+            su, sv = M.stream_block(u0, v0, a, b, c, T, R0, R1, lim=lim, emax=emax)
+            wu, wv = direct[lim]
+            assert (su[R0:R1].view(np.uint32) == wu[R0:R1].view(np.uint32)).all(), (R0, R1, lim)
+            assert (sv[R0:R1].view(np.uint32) == wv[R0:R1].view(np.uint32)).all(), (R0, R1, lim)
+            for s_ in range(T):
+                if s_ < lim:
+                    want = max(float(np.abs(direct[s_ + 1][0][R0:R1] - direct[s_][0][R0:R1]).max()),
+                               float(np.abs(direct[s_ + 1][1][R0:R1] - direct[s_][1][R0:R1]).max()))
+                    assert emax[s_] == want, (R0, R1, lim, s_)
+                else:
+                    assert emax[s_] == 0.0
