@@ -220,6 +220,7 @@ int hsflow_iterations_done(hsflow_t* h, int pair, int* done);  /* sweeps a pair 
                                                                    when hsflow_set_epsilon stopped it).  sync */
 int hsflow_effective_temporal_block(hsflow_t* h);
 int hsflow_sub_batch(hsflow_t* h);                    /* pairs per launch chosen by hsflow_configure          */
+int hsflow_device(hsflow_t* h);                       /* CUDA device the handle lives on                      */
 void* hsflow_alloc_pinned(size_t bytes);              /* cudaMallocHost / cudaFreeHost helpers     */
 void hsflow_free_pinned(void* p);
 

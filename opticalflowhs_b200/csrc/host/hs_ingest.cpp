@@ -81,7 +81,22 @@ struct Decoder {
         ok = batched != nullptr;
     }
 };
-Decoder& dec() { static Decoder d; return d; }
+// one decoder per device, created on first use with that device current (every entry point that takes a handle makes
+// the handle's device current first: use_device)
+constexpr int kMaxDevices = 64;
+Decoder& dec() {
+    static Decoder* d[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); dev = 0; }
+    if (!d[dev]) d[dev] = new Decoder();
+    return *d[dev];
+}
+int use_device(hsflow_t* h) {
+    const int dev = hsflow_device(h);
+    if (dev < 0) return fail(HSFLOW_EINVAL, "null handle");
+    CKC(cudaSetDevice(dev));
+    return HSFLOW_OK;
+}
 
 bool is_jpeg(const uint8_t* p, size_t n) { return n >= 2 && p[0] == 0xFF && p[1] == 0xD8; }
 
@@ -162,7 +177,13 @@ struct Pool {
     int device = 0;
     bool tried = false;
 };
-Pool& pool() { static Pool p; return p; }
+Pool& pool() {                                     // per device, like the decoder
+    static Pool* p[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); dev = 0; }
+    if (!p[dev]) p[dev] = new Pool();
+    return *p[dev];
+}
 
 int pool_threads() {
     const char* th = getenv("HSFLOW_NVJPEG_THREADS");
@@ -266,6 +287,7 @@ int hsingest_decode_to_device(const uint8_t* jpeg, size_t len, uint8_t* d_bgr, s
 
 int hsingest_load_pair_jpeg(hsflow_t* h, const uint8_t* j1, size_t n1, const uint8_t* j2, size_t n2, int* width, int* height) {
     if (!h) return fail(HSFLOW_EINVAL, "null handle");
+    { int rc0 = use_device(h); if (rc0) return rc0; }
     int w = 0, ht = 0, w2 = 0, h2 = 0;
     int rc;
     if ((rc = jpeg_info(j1, n1, &w, &ht, nullptr)) || (rc = jpeg_info(j2, n2, &w2, &h2, nullptr))) return rc;
@@ -284,6 +306,7 @@ int hsingest_load_pair_jpeg(hsflow_t* h, const uint8_t* j1, size_t n1, const uin
 
 int hsingest_load_pair_files(hsflow_t* h, const char* p1, const char* p2, int* width, int* height) {
     if (!h || !p1 || !p2) return fail(HSFLOW_EINVAL, "null argument");
+    { int rc0 = use_device(h); if (rc0) return rc0; }
     std::vector<uint8_t> b1, b2;
     if (!read_file(p1, b1)) return fail(HSFLOW_EINVAL, "cannot read %s", p1);
     if (!read_file(p2, b2)) return fail(HSFLOW_EINVAL, "cannot read %s", p2);
@@ -319,6 +342,7 @@ int hsingest_load_pair_files(hsflow_t* h, const char* p1, const char* p2, int* w
 
 int hsingest_push_frame_file(hsflow_t* h, const char* path) {
     if (!h || !path) return fail(HSFLOW_EINVAL, "null argument");
+    { int rc0 = use_device(h); if (rc0) return rc0; }
     std::vector<uint8_t> b;
     if (!read_file(path, b)) return fail(HSFLOW_EINVAL, "cannot read %s", path);
     uint8_t *d1 = nullptr, *d2 = nullptr;
@@ -351,6 +375,7 @@ int hsingest_run_jpeg_batch(hsflow_t* h, const uint8_t* const* jpegs, const size
     const int n_pairs = sequence ? n_images - 1 : n_images / 2;
     if (n_pairs < 1 || (!sequence && (n_images & 1))) return fail(HSFLOW_EINVAL, "need an even number of images (pairs) or >= 2 consecutive frames");
     if (sample_step < 0) return fail(HSFLOW_EINVAL, "sample_step must be >= 0");
+    { int rc0 = use_device(h); if (rc0) return rc0; }
     Decoder& D = dec();
     if (!D.ok) return fail(HSFLOW_ENODEV, "nvJPEG initialisation failed (no CUDA device?)");
     int w = 0, ht = 0;

@@ -1537,6 +1537,7 @@ int hsflow_iterations_done(hsflow_t* h, int pair, int* done) {
     return HSFLOW_OK;
 }
 int hsflow_effective_temporal_block(hsflow_t* h) { return h ? effective_T(h) : 0; }
+int hsflow_device(hsflow_t* h) { return h ? h->device : -1; }
 
 void* hsflow_alloc_pinned(size_t bytes) {
     void* p = nullptr;

@@ -85,6 +85,7 @@ SIGNATURES = {
     "hsflow_iterations_done": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "hsflow_effective_temporal_block": (C.c_int, [_P]),
     "hsflow_sub_batch": (C.c_int, [_P]),
+    "hsflow_device": (C.c_int, [_P]),
     "hsflow_alloc_pinned": (_P, [C.c_size_t]),
     "hsflow_free_pinned": (None, [_P]),
 }
