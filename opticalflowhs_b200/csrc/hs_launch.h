@@ -119,8 +119,12 @@ cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long l
 
 // temporally blocked streaming kernel (hs_stream.cu)
 constexpr int kMaxT = 8;
-constexpr int kDefaultT = 6;           // temporal_block = 0: fastest sustained depth on B200 (profiles/README.md, T sweep)
-constexpr int kSmallT = 4;             // ... when the job cannot fill the GPU twice over: shorter warm-up, shorter units
+// temporal_block = 0 (auto), three regimes (profiles/README.md, round-2 T sweeps on the final build):
+constexpr int kBigT = 8;               // >= kBigPixels per launch: 256 4K pairs 1 051 k against 1 019 k at T = 6 -- the deeper block moves
+                                       // 25 % less HBM traffic, draws less power and lets the SM clock rise from 1.54 to 1.73 GHz under the cap
+constexpr int kDefaultT = 6;           // one to three 4K pairs (one pair: 833 k at T = 6, 803 k at T = 8), and every strip of a sharded frame
+constexpr int kSmallT = 4;             // the job cannot fill the GPU twice over: shorter warm-up, shorter units (1080p: 573 k against 496 k at T = 6)
+constexpr long long kBigPixels = 24LL << 20;   // ~ three 4K pairs
 StreamGeom stream_geometry(int T);
 cudaError_t stream_prepare(int device);     // opt in to large dynamic shared memory for every instantiation
 int stream_warps_per_sm(int T, int stencil);   // resident warps (= CTAs) per SM (occupancy API)

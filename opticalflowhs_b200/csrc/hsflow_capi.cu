@@ -208,7 +208,16 @@ static int auto_T(const hsflow* h) {
     const StreamGeom G = stream_geometry(kDefaultT);
     const long long nsx = (h->W + G.valid_w - 1) / G.valid_w;
     const long long units = nsx * ((h->H + 4 * kDefaultT - 1) / (4 * kDefaultT)) * std::max(1, std::min(h->P, h->S));
-    return units >= 2LL * h->sm_count * 8 ? kDefaultT : kSmallT;
+    if (units < 2LL * h->sm_count * 8) return kSmallT;
+    const long long px = (long long)h->W * h->H * std::max(1, std::min(h->P, h->S));
+    return px >= kBigPixels ? kBigT : kDefaultT;
+}
+// Iterations of the next launch when `left` remain and blocks hold at most T: the ceil(left / T) launches are made as
+// equal as possible (100 iterations at T = 8: 9 x 8 + 4 x 7 instead of 12 x 8 + 4, whose last block would run at the
+// speed of the shallow T = 4 instantiation).  Any partition gives the same bits: streaming == direct sweeps.
+static int next_block(int left, int T) {
+    const int blocks = (left + T - 1) / T;
+    return (left + blocks - 1) / blocks;
 }
 // LITERAL mode (update_v = 0: the shipped u_v_updateKernel never writes v, Kernels.cl:87-89) on the FULL streaming
 // kernel.  While v is identically zero, "v stays what it was" and "v' = vbar - b t with b = 0" are the same thing, and
@@ -828,7 +837,7 @@ int hsflow_iterate(hsflow_t* h, int n) {
         // they finished reading the buffer our next launch stores into.
         if (!use_stream_kernel(h, 1)) return fail(HSFLOW_EINVAL, "peer transport needs the streaming kernel (FAST math, update_v = 1)");
         while (n > 0) {
-            const int t = std::min(n, T);
+            const int t = next_block(n, T);
             const int lo = h->top_edge ? 0 : t, hi = h->bottom_edge ? h->H : h->H - t;
             if ((h->has_peer[0] && h->push_lo[0] < t) || (h->has_peer[1] && h->H - h->push_hi[1] < t) || lo >= hi)
                 return fail(HSFLOW_EINVAL, "strip has fewer ghost rows than the temporal block (%d)", t);
@@ -850,7 +859,7 @@ int hsflow_iterate(hsflow_t* h, int n) {
     const int sweeps_at_end = h->sweeps + n;
     { int rc = eps_guard(h); if (rc) return rc; }
     while (n > 0) {
-        const int t = std::min(n, T);
+        const int t = next_block(n, T);
         const int lo = h->top_edge ? 0 : h->valid_lo + t;
         const int hi = h->bottom_edge ? h->H : h->valid_hi - t;
         if (lo >= hi) return fail(HSFLOW_EINVAL, "ghost rows exhausted: refresh the halo (valid rows [%d,%d), block %d)", h->valid_lo, h->valid_hi, t);
@@ -894,7 +903,7 @@ static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nu
                             float* fin_u = nullptr, float* fin_v = nullptr) {
     const int T = effective_T(h), N = h->iterations;
     int L = 0;                                     // ping-pong flips
-    for (int left = N; left > 0;) { const int t = std::min(left, T); L += use_stream_kernel(h, t) ? 1 : t; left -= t; }
+    for (int left = N; left > 0;) { const int t = next_block(left, T); L += use_stream_kernel(h, t) ? 1 : t; left -= t; }
     const int norm = h->math == HSFLOW_MATH_FAST ? 1 : 0;
     h->coef_zero_b = (!h->update_v && use_stream_kernel(h, 1)) ? 1 : 0;     // u, v are zeroed below: only warm / dirty say no
     int rc = run_deriv(h, p0, n, norm, h->c0, h->c1, h->c2, h->c_rp, h->c_pp, f1base, f2base);
@@ -910,7 +919,7 @@ static int compute_subbatch(hsflow* h, int p0, int n, const uint8_t* f1base = nu
     int sweep = 0;
     if (h->eps > 0.0 && (rc = eps_reset(h, p0, n))) return rc;
     for (int left = N; left > 0;) {
-        const int t = std::min(left, T);
+        const int t = next_block(left, T);
         if (use_stream_kernel(h, t)) {
             if (left == t) { h->ov_u = fin_u; h->ov_v = fin_v; }
             h->ec_on = h->eps > 0.0; h->ec_sweep = N - left; h->ec_off = p0;
