@@ -370,7 +370,7 @@ def run_ours(args, rank, world, local_rank):
     def time_e2e(call):
         call()                                       # warm-up (allocations, first touch)
         barrier()
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 5))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             call()                                   # returns when the results are in host memory
@@ -463,7 +463,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline_opencv": cpu_cv,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W4K * H4K * ep * world,
                     "d2h_bytes_per_step": 8 * W4K * H4K * ep * world, "pairs_per_step": ep * world, "api": "hsflow_run_batch_host",
-                    "host_numa_node_rank0": numa_node, "parity": e2e_parity, "gpu_launches_per_step": l_e2e // (1 + max(1, min(args.steps, 3))),
+                    "host_numa_node_rank0": numa_node, "parity": e2e_parity, "gpu_launches_per_step": l_e2e // (1 + max(1, min(args.steps, 5))),
                     "wire": wire, "wire_bound_value": wire_bound,
                     "frac_of_wire_bound": (e2e_value / wire_bound) if wire_bound else None,
                     "sampled": {"value": e2e_sampled, "unit": UNIT, "api": "hsflow_run_pipeline_host(sample_step=4)",
