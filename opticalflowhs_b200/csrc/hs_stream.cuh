@@ -179,6 +179,11 @@ static __device__ __noinline__ void peer_push_row(const StreamArgs* __restrict__
     }
 }
 
+#ifndef HS_TRIP_UNROLL
+#define HS_TRIP_UNROLL 1           // experiments: 2 = two trips of the steady-state loop per iteration of the compiled loop
+#endif
+constexpr int kTripUnroll = HS_TRIP_UNROLL;
+
 // ---- the kernel -----------------------------------------------------------------------------------
 #ifndef HS_STREAM_MIN_CTAS
 #define HS_STREAM_MIN_CTAS 1     // experiments: 3 caps the kernel at 168 registers (12 warps per SM)
@@ -533,7 +538,7 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
         float* uo_row = uo + (size_t)(r - T) * A.row_pitch;    // advanced by one row per tick
         float* vo_row = vo + (size_t)(r - T) * A.row_pitch;
         unsigned orow = (unsigned)(r - T - R0);                // output row of the tick relative to the chunk
-#pragma unroll 1
+#pragma unroll kTripUnroll
         for (; r + RG - 1 <= r_end; r += RG) {
             mbar_wait(ubar, upar);
             mbar_wait(cbar, cpar);
