@@ -46,7 +46,7 @@ int hsingest_push_frame_file(hsflow_t* h, const char* path);
  * decode of the next chunk of pairs (host-side Huffman stage included) overlaps the engine's compute of the current
  * chunk: the handle's pair slots are used as two halves.  u_out / v_out: n_pairs fields of W*H floats, or with
  * sample_step > 0 the stride-`step` samples (ceil(H/step) x ceil(W/step) floats per pair, see hsflow_sample_uv).
- * Uses the handle's parameters (hsflow_set_params ...); reconfigures it.  stats (may be NULL) receives
+ * Uses the handle's parameters (hsflow_set_params ...); reconfigures it and resets hsflow_set_tuning to automatic.  stats (may be NULL) receives
  * {decode_ms_total, images decoded, pairs per chunk, nvjpegBackend_t used + host threads / 100}. */
 int hsingest_run_jpeg_batch(hsflow_t* h, const uint8_t* const* jpegs, const size_t* sizes, int n_images, int sequence,
                             int sample_step, float* u_out, float* v_out, double stats[4]);
