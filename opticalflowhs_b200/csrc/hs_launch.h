@@ -119,10 +119,13 @@ cudaError_t launch_dot_mask(const float* u, const float* v, int W, int H, long l
 
 // temporally blocked streaming kernel (hs_stream.cu)
 constexpr int kMaxT = 8;
-// temporal_block = 0 (auto), three regimes (profiles/README.md, round-2 T sweeps on the final build):
-constexpr int kBigT = 8;               // >= kBigPixels per launch: 256 4K pairs 1 051 k against 1 019 k at T = 6 -- the deeper block moves
-                                       // 25 % less HBM traffic, draws less power and lets the SM clock rise from 1.54 to 1.73 GHz under the cap
-constexpr int kDefaultT = 6;           // one to three 4K pairs (one pair: 833 k at T = 6, 803 k at T = 8), and every strip of a sharded frame
+// temporal_block = 0 (auto), three regimes (profiles/README.md, round-2 T sweeps on the final build, sustained under the 1000 W cap):
+constexpr int kBigT = 7;               // >= kBigPixels per launch.  256 4K pairs: T = 6 / 7 / 8 = 1 040 / 1 075 / 1 065 k, 64 pairs 1 013 / 1 045 / 1 023 k,
+                                       // a 16384^2 frame 125.2 / 121.6 / 124.3 ms per 500 iterations: the deeper block moves less HBM traffic, draws
+                                       // less power and lets the SM clock rise (1.55 -> 1.64 -> 1.75 GHz); T = 8 no longer fits 255 registers
+                                       // with the scalar pipeline state (hs_stream.cuh) and pays 12 % register moves in its packed form
+constexpr int kDefaultT = 6;           // one to three 4K pairs (one pair: 842 k at T = 6), and every strip of a sharded frame (2048-row strip: 7.51 ms
+                                       // per 240 iterations at T = 6, 7.90 at T = 7)
 constexpr int kSmallT = 4;             // the job cannot fill the GPU twice over: shorter warm-up, shorter units (1080p: 573 k against 496 k at T = 6)
 constexpr long long kBigPixels = 24LL << 20;   // ~ three 4K pairs
 StreamGeom stream_geometry(int T);

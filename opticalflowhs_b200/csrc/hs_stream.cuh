@@ -179,6 +179,9 @@ static __device__ __noinline__ void peer_push_row(const StreamArgs* __restrict__
     }
 }
 
+#ifndef HS_SCALAR_STATE_MAX_T
+#define HS_SCALAR_STATE_MAX_T 7    // deepest block whose pipeline state is kept as scalar halves (see k_jacobi_stream)
+#endif
 #ifndef HS_TRIP_UNROLL
 #define HS_TRIP_UNROLL 1           // experiments: 2 = two trips of the steady-state loop per iteration of the compiled loop
 #endif
@@ -308,11 +311,22 @@ k_jacobi_stream(const __grid_constant__ CUtensorMap tm_uv, const __grid_constant
 
     // register pipeline: per stage and field two partial sums per pixel, held as packed pixel pairs
     // (index 0: u of pixels 0,1; 1: u of pixels 2,3; 2, 3: v likewise) for FFMA2 / FADD2 / FMUL2
-    f32x2 p[T][4], g[T][4];
+    // The loop-carried state is held as SCALAR halves and packed where an FFMA2 / FADD2 / FMUL2 consumes it: ptxas cannot
+    // coalesce the copies of 64-bit register PAIRS across the loop back edge (alignment of the pair), which left 65 (T = 6)
+    // to 99 (T = 8) register moves per trip; with scalar halves 8 remain and the trip shrinks from 895 to 838 instructions
+    // (T = 6: 990 -> 1 011 k Mpixel-iterations/s sustained).  At T = 8 the scalar form needs more than 255 registers
+    // (120 bytes of spills inside the loop, 1 012 -> 990 k), so the deepest block keeps the packed form.
+    struct F2 {
+        float lo, hi;
+        __device__ __forceinline__ operator f32x2() const { return pk2(lo, hi); }
+        __device__ __forceinline__ F2& operator=(f32x2 v) { unpk2(v, lo, hi); return *this; }
+    };
+    using State = typename std::conditional<(T <= HS_SCALAR_STATE_MAX_T), F2, f32x2>::type;
+    State p[T][4], g[T][4];
 #pragma unroll
     for (int s = 0; s < T; ++s)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { p[s][j] = 0ull; g[s][j] = 0ull; }
+        for (int j = 0; j < 4; ++j) { p[s][j] = (f32x2)0ull; g[s][j] = (f32x2)0ull; }
 
     const bool lane_out = (lane >= C::HL / 4) && (lane < 32 - C::HL / 4) && (col0 < W);
     // TRACK: what each stage received one tick ago (= the old value of the row it puts out now) and its running

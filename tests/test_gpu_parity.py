@@ -754,17 +754,17 @@ def test_full_size_frame_windows_against_oracle_crops(P, oracle, W, H, N, T):
 
 def test_bench_geometry_batch_windows_against_oracle_crops(P, oracle):
     """The timed configuration of bench.py (BASELINE.json configs[3]): 4K pairs, 100 iterations, FULL mode, automatic
-    temporal block (8), MANY pairs in ONE launch (pair coordinate z up to 47, several waves of work units).  Windows
+    temporal block (7), MANY pairs in ONE launch (pair coordinate z up to 47, several waves of work units).  Windows
     of the first, a middle and the last pair -- at corners, on strip seams (multiples of 112 columns) and on row-chunk
     seams -- against the oracle on their domains of dependence."""
     W, H, N, K, pairs, seed0 = 3840, 2160, 100, 40, 48, 1234
     with P.HSFlow(0) as e:
         e.set_params(15.0, N, P.STENCIL_CL8, True, 0)
         e.configure(W, H, pairs).synth_frames(0, 0, seed0)
-        assert e.sub_batch == pairs and e.temporal_block == 8       # throughput regime: the deepest block
+        assert e.sub_batch == pairs and e.temporal_block == 7       # throughput regime: the deep block
         l0 = e.kernel_launches
         e.compute()
-        assert e.kernel_launches - l0 == 1 + (N + 7) // 8          # one derivative launch + 13 blocks (9 x 8 + 4 x 7) over all pairs
+        assert e.kernel_launches - l0 == 1 + (N + 6) // 7          # one derivative launch + 15 blocks (10 x 7 + 5 x 6) over all pairs
         fields = {z: e.read_uv(z) for z in (0, pairs // 2 + 1, pairs - 1)}
     spots = [(0, 0), (H - K, W - K), (H // 2 - K // 2, 9 * 112 - K // 2), (3 * 24 - K // 2, 20 * 112 - K // 2), (1111, 1777)]
     for z, (u, v) in fields.items():
@@ -805,7 +805,7 @@ def test_16k_frame_500_iterations_windows_against_oracle_crops(P, oracle):
     with P.HSFlow(0) as e:
         e.set_params(15.0, N, P.STENCIL_CL8, True, 0)
         e.configure(W, H, 1).synth_frames(0, 0, 1234).compute()
-        assert e.temporal_block == 8
+        assert e.temporal_block == 7
         u, v = e.read_uv()
     assert np.isfinite(u[::7, ::5]).all() and np.isfinite(v[::7, ::5]).all()
     spots = [(0, 0), (H - K, W - K), (2049 - K // 2, 73 * 112 - K // 2), (H // 2 + 3, W // 3)]
