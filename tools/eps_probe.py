@@ -14,7 +14,7 @@ W, H, N = int(os.environ.get("W", 3840)), int(os.environ.get("H", 2160)), int(os
 PAIRS = int(os.environ.get("NP", 1))
 for mode in ("cv", "cl"):
     rows = {}
-    for kernel, name in ((1, "single-sweep + check per iteration"), (0, "blocked TRACK kernel (T = 4) + replay")):
+    for kernel, name in ((1, "single-sweep + check per iteration"), (0, "blocked TRACK kernel + replay")):
         with P.HSFlow(0) as e:
             e.set_kernel(kernel)
             if mode == "cv":
